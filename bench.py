@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the BitDelta hot path on B200: Mistral-7B + 6 deltas, batched decode (BASELINE.json metric).
+
+A "step" is one decode step's worth of the hot path: all 224 BinaryDiff linears of Mistral-7B (32 layers x
+q/k/v/o/gate/up/down) evaluated for 6 tenants x 1 new token through `DiffCompressModule.forward`
+(demo/demo_backend.py:93-98 semantics), i.e. 224 launches of the fused kernel reading 13.96 GB of bf16 base weights and
+6 x 0.87 GB of sign words.  Attention, norms and the per-tenant lm_heads are not part of the W1A16 path and are not
+executed; the config says so.  Weights are random-init, inputs synthetic.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): every rank holds a replica of W_base and serves its own 6 tenants (tenant sharding,
+no collective on the data path) -> weak scaling; value = 6*N tokens / max-over-ranks step time.
+
+`--impl reference` times the reference's CPU path for the same workload (the oracle's C port of the unpack-matmul
+path, all host threads) on a bounded sample -- one decoder layer per step -- and scales it to a whole decode step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Mistral-7B decoder layer: (name, N_out, K_in)
+MISTRAL_LINEARS = [
+    ("q_proj", 4096, 4096), ("k_proj", 1024, 4096), ("v_proj", 1024, 4096), ("o_proj", 4096, 4096),
+    ("gate_proj", 14336, 4096), ("up_proj", 14336, 4096), ("down_proj", 4096, 14336),
+]
+LAYERS = 32
+TENANTS = 6
+
+
+def step_bytes(T: int, m: int, layers: int = LAYERS) -> int:
+    """Algorithmic bytes of one step: 2NK + T*NK/8 + 2*T*m*(K+N) per linear."""
+    per_layer = sum(2 * n * k + T * n * k // 8 + 2 * T * m * (k + n) for _, n, k in MISTRAL_LINEARS)
+    return per_layer * layers
+
+
+def step_flops(T: int, m: int, layers: int = LAYERS) -> int:
+    return sum(4 * T * m * n * k for _, n, k in MISTRAL_LINEARS) * layers
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = the upper half of the samples (the sampler also sees idle time around the region)
+        sm.sort()
+        load = sm[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_layer_sample(threads: int = 0, reps: int = 1, seed: int = 0):
+    """Times the oracle's C port on ONE Mistral decoder layer (7 linears, 6 tenants, 1 token each) on the host cores.
+    Returns (seconds per layer, cores used).  Only bench.py's baseline legs may execute oracle/ code."""
+    import numpy as np
+
+    from oracle import c_oracle as C
+
+    rng = np.random.default_rng(seed)
+    probs = []
+    for _, n, k in MISTRAL_LINEARS:
+        x = (rng.integers(0, 1 << 14, (TENANTS, 1, k)).astype(np.uint16)) | 0x3C00       # bf16 in [1, 2)
+        w = (rng.integers(0, 1 << 14, (n, k)).astype(np.uint16)) | 0x3800
+        masks = rng.integers(-(2**31), 2**31 - 1, (TENANTS, k // 32, n)).astype(np.int32)
+        coeff = np.full(TENANTS, 0.002, np.float32)
+        probs.append((x, w, masks, coeff))
+    cores = threads or C.max_threads()
+    C.fwd_batched_bf16(*probs[1], threads=threads)  # warm the thread pool / page in
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for p in probs:
+            C.fwd_batched_bf16(*p, threads=threads)
+        times.append(time.perf_counter() - t0)
+    return min(times), cores
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    t_layers = []
+    for i in range(args.warmup + args.steps):
+        t, cores = cpu_layer_sample(threads=0, reps=1, seed=i)
+        if i >= args.warmup:
+            t_layers.append(t)
+    t_step = statistics.mean(t_layers) * LAYERS
+    value = TENANTS / t_step
+    sample = f"1 of {LAYERS} decoder layers per step (7 linears x {TENANTS} tenants x 1 token), scaled x{LAYERS}"
+    line = {
+        "impl": "reference", "metric": "tokens/sec Mistral-7B+6delta batched decode (BinaryDiff linears)", "value": value,
+        "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world: int):
+    return {
+        "workload": "mistral7b_6delta_decode_linears",
+        "detail": f"{LAYERS} layers x 7 BinaryDiff linears, {TENANTS} tenants x 1 token per GPU, hidden 4096 / inter 14336 / kv 1024",
+        "tenants_per_gpu": TENANTS, "tokens_per_step_per_gpu": TENANTS, "parallelism": f"tenant-sharded x{world} (no collective)",
+        "l2_policy": "inputs larger than L2 (19.2 GB of weights+signs streamed per step)",
+        "not_included": "attention, norms, per-tenant lm_head (outside the W1A16 path)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_model(torch, bd, dev, layers: int, seed: int):
+    """Random-init Mistral-7B-shaped stack of DiffCompressModules on `dev`."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    mods = []
+    for _ in range(layers):
+        layer = {}
+        for name, n, k in MISTRAL_LINEARS:
+            lin = torch.nn.Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16)
+            with torch.no_grad():
+                lin.weight.normal_(0.0, 0.02, generator=gen)
+            masks = torch.randint(-(2**31), 2**31 - 1, (TENANTS, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            coeffs = (torch.rand(TENANTS, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
+            layer[name] = bd.DiffCompressModule(lin, masks, coeffs)
+        mods.append(layer)
+    return mods
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+
+    import bitdelta_b200 as bd
+    from bitdelta_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    layers = args.layers
+    mods = build_model(torch, bd, dev, layers, seed=1234 + rank)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    # static synthetic activations (one new token per tenant); outputs are not chained because the omitted norms
+    # would be needed to keep magnitudes bounded
+    x_h = torch.randn(TENANTS, 1, 4096, generator=gen, device=dev).bfloat16()
+    x_a = torch.randn(TENANTS, 1, 4096, generator=gen, device=dev).bfloat16()
+    x_m = torch.randn(TENANTS, 1, 14336, generator=gen, device=dev).bfloat16()
+    host_in = [t.cpu().pin_memory() for t in (x_h, x_a, x_m)]
+    host_out = torch.empty(TENANTS, 1, 4096, dtype=torch.bfloat16).pin_memory()
+
+    def step():
+        y = None
+        for layer in mods:
+            layer["q_proj"](x_h); layer["k_proj"](x_h); layer["v_proj"](x_h)
+            layer["o_proj"](x_a)
+            layer["gate_proj"](x_h); layer["up_proj"](x_h)
+            y = layer["down_proj"](x_m)
+        return y
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        y_eager = step()  # also sizes the workspace on this stream
+        torch.cuda.synchronize(dev)
+        n0 = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            y_static = step()
+        launches_per_step = _lib.launch_count() - n0
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        assert torch.equal(y_static, y_eager), "graph replay disagrees with eager execution"
+
+        def barrier():
+            torch.cuda.synchronize(dev)
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        # ---- device-resident timing -------------------------------------------------------------------------
+        for _ in range(args.warmup):
+            graph.replay()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            graph.replay()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, every step ------------------
+        def e2e_step():
+            x_h.copy_(host_in[0], non_blocking=True)
+            x_a.copy_(host_in[1], non_blocking=True)
+            x_m.copy_(host_in[2], non_blocking=True)
+            graph.replay()
+            host_out.copy_(y_static, non_blocking=True)
+            stream.synchronize()  # the caller needs the tokens before it can build the next step
+
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record(stream)
+        barrier()
+        ms_e2e_total = f0.elapsed_time(f1)
+
+    times = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_step = times[0].item() / args.steps
+    ms_e2e = times[1].item() / args.steps
+
+    if rank == 0:
+        tokens = TENANTS * world
+        value = tokens / (ms_step * 1e-3)
+        e2e_value = tokens / (ms_e2e * 1e-3)
+        hbm_peak, tf_peak, peak_kind = measured_peaks()
+        bytes_step = step_bytes(TENANTS, 1, layers)
+        achieved = bytes_step / (ms_step * 1e-3) / 1e9
+        kernel = {1: "simt", 2: "umma"}[_lib.lib.bd_select_kernel(0, TENANTS, 1, 4096, 4096, 1)]
+        cpu = None
+        if not args.no_cpu_baseline:
+            t_layer, cores = cpu_layer_sample(threads=0, reps=2)
+            cpu = {"value": TENANTS / (t_layer * LAYERS), "unit": "tokens/s", "cores": cores, "kind": "port",
+                   "sample": f"1 of {LAYERS} decoder layers (7 linears x {TENANTS} tenants x 1 token), best of 2, scaled x{LAYERS}"}
+        cfg = workload_config(world)
+        cfg["kernel"] = kernel
+        if layers != LAYERS:
+            cfg["workload"] += f"_{layers}layers_DEBUG"
+        line = {
+            "metric": "tokens/sec Mistral-7B+6delta batched decode (BinaryDiff linears)",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(t.numel() * 2 for t in host_in), "d2h_bytes_per_step": host_out.numel() * 2},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": f"bd fused forward ({kernel})",
+                         "algorithmic_bytes_per_step": bytes_step, "launches_per_step": launches_per_step,
+                         "w1a16_tflops": step_flops(TENANTS, 1, layers) / (ms_step * 1e-3) / 1e12,
+                         "w1a16_frac_of_bf16_peak": step_flops(TENANTS, 1, layers) / (ms_step * 1e-3) / 1e12 / tf_peak},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers (the result is labelled DEBUG)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+"""Drop-in for the multi-tenant modules of the reference's ``demo/demo_backend.py`` (lines 62-179).
+
+    DataParallelModule(module, weight_list)                reference :62-79
+    DiffCompressModule(module, mask_list, coeff_list)      reference :82-98
+    register_diff_compress / unregister_diff_compress      reference :107-166
+    DiffCompress (context manager)                         reference :170-179
+
+Convention kept from the reference (:101-102): batch size == number of checkpoints, and batch row ``i`` is served by
+checkpoint ``i``.  ``DiffCompressModule.forward`` is one launch of the fused batched kernel: the shared base product
+and all tenants' 1-bit deltas, with the per-tenant coefficient applied in the fp32 epilogue (the reference's
+"TODO: Fuse coeff", :96).  The FastAPI server, prompt templating and tokenizers of the demo are out of scope.
+"""
+from __future__ import annotations
+
+import gc
+
+import torch
+import torch.nn as nn
+
+from .diff import _fused_forward
+
+
+class DataParallelModule(nn.Module):
+    """Per-tenant full-precision leaf (embed_tokens, RMSNorm, lm_head): row i uses ``weight_list[i]`` (:62-79).
+
+    Outputs of different width (ragged vocabularies) are right-padded with ``finfo(dtype).min`` exactly like the
+    reference's nested-tensor padding (:78-79).
+    """
+
+    def __init__(self, module, weight_list):
+        super().__init__()
+        self.module = module
+        self.weight_list = weight_list
+        self.original_weight = module.weight.data
+
+    def forward(self, hidden_states):
+        outputs = []
+        for i in range(len(self.weight_list)):
+            self.module.weight.data = self.weight_list[i]
+            outputs.append(self.module(hidden_states[i, None])[0])
+        width = max(o.shape[-1] for o in outputs)
+        if all(o.shape[-1] == width for o in outputs):
+            return torch.stack(outputs, dim=0)
+        out = outputs[0].new_full((len(outputs),) + tuple(outputs[0].shape[:-1]) + (width,), torch.finfo(outputs[0].dtype).min)
+        for i, o in enumerate(outputs):
+            out[i, ..., : o.shape[-1]] = o
+        return out
+
+
+class DiffCompressModule(nn.Module):
+    """Shared ``nn.Linear`` + per-tenant 1-bit deltas (:82-98): ``y[t] = module(x[t]) + coeff[t] * (x[t] . sign_t)``."""
+
+    kernel = "auto"
+
+    def __init__(self, module, mask_list, coeff_list):
+        super().__init__()
+        self.module = module
+        self.mask = mask_list    # int32 [T, K/32, N], stacked once by register_diff_compress
+        self.coeff = coeff_list  # [T], model dtype or fp32
+
+    def forward(self, hidden_states):
+        # hidden_states: (T, seq, K)
+        T = self.mask.shape[0]
+        assert hidden_states.dim() == 3 and hidden_states.shape[0] == T, "Incompatible batch dimensions"
+        x = hidden_states.contiguous()
+        w = self.module.weight
+        if not w.is_contiguous():
+            w = w.contiguous()
+        y = _fused_forward(x, w, self.mask, self.coeff, T, self.kernel)
+        if getattr(self.module, "bias", None) is not None:
+            y = y + self.module.bias
+        return y
+
+
+# Assume batch size = len(checkpoint_list); sample i uses checkpoint_list[i].
+# Cache of stacked masks / coeffs, keyed by module path (reference :105).
+cached_modules = {}
+
+
+def register_diff_compress(model, checkpoint_list):
+    """Wrap every leaf whose name appears in the checkpoints (reference :107-153).
+
+    ``<name>.weight`` in the checkpoint -> DataParallelModule over the tenants' full weights;
+    ``<name>.mask``   in the checkpoint -> DiffCompressModule over stacked masks ``[T,K/32,N]`` and coeffs ``[T]``
+    (stacked once, cached in ``cached_modules`` and popped from the per-tenant dicts to free memory).
+    """
+    for name, module in list(model.named_modules()):
+        if len(list(module.named_children())) != 0:
+            continue
+        parent = model.get_submodule(".".join(name.split(".")[:-1]))
+        leaf = name.split(".")[-1]
+        if f"{name}.weight" in checkpoint_list[0]:
+            setattr(parent, leaf, DataParallelModule(module, [ckpt[f"{name}.weight"] for ckpt in checkpoint_list]))
+        elif f"{name}.mask" in checkpoint_list[0] or name in cached_modules:
+            assert isinstance(module, nn.Linear), "Only support linear layer"
+            if name not in cached_modules:
+                cached_modules[name] = (
+                    torch.stack([ckpt[f"{name}.mask"] for ckpt in checkpoint_list], dim=0).contiguous(),
+                    torch.stack([ckpt[f"{name}.coeff"] for ckpt in checkpoint_list], dim=0),
+                )
+                for ckpt in checkpoint_list:
+                    ckpt.pop(f"{name}.mask")
+                    ckpt.pop(f"{name}.coeff")
+                gc.collect()
+                if torch.cuda.is_available():
+                    torch.cuda.empty_cache()
+            setattr(parent, leaf, DiffCompressModule(module, cached_modules[name][0], cached_modules[name][1]))
+
+
+def unregister_diff_compress(model):
+    """Undo register_diff_compress (reference :156-166)."""
+    for name, module in list(model.named_modules()):
+        if isinstance(module, DataParallelModule):
+            module.module.weight.data = module.original_weight
+            parent = model.get_submodule(".".join(name.split(".")[:-1]))
+            setattr(parent, name.split(".")[-1], module.module)
+        elif isinstance(module, DiffCompressModule):
+            parent = model.get_submodule(".".join(name.split(".")[:-1]))
+            setattr(parent, name.split(".")[-1], module.module)
+
+
+class DiffCompress:
+    """Context manager form (reference :170-179)."""
+
+    def __init__(self, model, checkpoint_list):
+        self.model = model
+        self.checkpoint_list = checkpoint_list
+
+    def __enter__(self):
+        register_diff_compress(self.model, self.checkpoint_list)
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        unregister_diff_compress(self.model)

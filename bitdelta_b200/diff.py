@@ -1,0 +1,203 @@
+"""Drop-in for the reference module ``bitdelta/diff.py``: ``BinaryDiff`` and the ``diff.pt`` glue.
+
+    BinaryDiff(base, finetune)        reference diff.py:8-39   (buffers mask/base, parameter coeff, forward(x))
+    compress_diff / save_diff / load_diff / save_full_model   reference diff.py:41-116
+
+``BinaryDiff.forward`` is ONE launch of the fused sm_100a kernel
+``y = x.W_base^T + coeff * (x . (2*unpack(mask)-1))`` instead of the reference's mask.repeat copy + cuBLAS GEMM +
+Triton bmm + two pointwise kernels (diff.py:38-39).  The sign matrix is never repeated per batch row: the kernel
+broadcasts it (tenant stride 0).
+"""
+from __future__ import annotations
+
+import gc
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .binary_gemm_kernel import pack, unpack  # noqa: F401  (re-exported like the reference module)
+
+
+def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coeff: torch.Tensor, T: int, kernel="auto") -> torch.Tensor:
+    """x: (T, m, K) contiguous; w_nk: (N, K) contiguous; masks: (K/32, N) or (T, K/32, N) int32; coeff: (T,) or 0-dim."""
+    if not x.is_cuda:
+        raise RuntimeError(
+            "bitdelta_b200: the fused BinaryDiff forward is implemented only as sm_100a CUDA kernels "
+            f"(libbitdelta_b200.so); got activations on {x.device}. There is no CPU fallback."
+        )
+    m, K = x.shape[1], x.shape[2]
+    N = w_nk.shape[0]
+    assert w_nk.shape[1] == K and masks.shape[-2] * 32 == K and masks.shape[-1] == N, "Incompatible dimensions"
+    assert x.dtype == w_nk.dtype, "activations and base weight must share a dtype"
+    assert masks.dtype == torch.int32 and masks.is_contiguous()
+    assert x.device == w_nk.device == masks.device == coeff.device, "A and B must be on the same device"
+    stride = masks.shape[-2] * masks.shape[-1] if masks.dim() == 3 else 0
+    if masks.dim() == 3:
+        assert masks.shape[0] == T, "Incompatible batch dimensions"
+    if coeff.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        coeff = coeff.float()
+    coeff = coeff.detach().reshape(-1)
+    if coeff.numel() == 1 and T > 1:
+        coeff = coeff.expand(T)
+    coeff = coeff.contiguous()
+    assert coeff.numel() == T
+    y = torch.empty((T, m, N), device=x.device, dtype=x.dtype)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(x.device, T * m, N)
+        _lib.check(
+            _lib.lib.bd_binarydiff_fwd_batched(
+                x.data_ptr(), w_nk.data_ptr(), masks.data_ptr(), coeff.data_ptr(), _lib.dtype_code(coeff.dtype), y.data_ptr(),
+                _lib.dtype_code(x.dtype), T, m, K, N, stride, ws.data_ptr(), ws.numel(), _lib.kernel_code(kernel),
+                _lib.stream_ptr(x.device),
+            )
+        )
+    return y
+
+
+class BinaryDiff(nn.Module):
+    """16-bit base weight + 1-bit delta linear layer (reference ``BinaryDiff``, diff.py:8-39).
+
+    State: ``mask`` int32 ``[K/32, N]`` (buffer), ``base`` = ``W_base.T`` ``[K, N]`` stride ``(1, K)`` view (buffer),
+    ``coeff`` fp32 0-dim ``nn.Parameter`` -- identical names, shapes and dtypes, so ``state_dict`` and ``save_diff``
+    output are interchangeable with the reference's.
+    """
+
+    kernel = "auto"
+
+    def __init__(self, base: torch.Tensor, finetune: torch.Tensor):
+        super().__init__()
+        assert base.shape == finetune.shape and base.dim() == 2
+        N, K = base.shape
+        assert K % 32 == 0, "K must be divisible by n_bits"
+        if base.is_cuda and base.dtype in (torch.bfloat16, torch.float16):
+            base_c = base.contiguous()
+            fine_c = finetune.to(base.device, base.dtype).contiguous()
+            mask = torch.empty((K // 32, N), dtype=torch.int32, device=base.device)
+            quantile = torch.empty((), dtype=torch.float32, device=base.device)
+            scratch = torch.zeros((), dtype=torch.float64, device=base.device)
+            with torch.cuda.device(base.device):
+                _lib.check(
+                    _lib.lib.bd_compress(
+                        base_c.data_ptr(), fine_c.data_ptr(), _lib.dtype_code(base.dtype), N, K, mask.data_ptr(),
+                        quantile.data_ptr(), scratch.data_ptr(), _lib.stream_ptr(base.device),
+                    )
+                )
+            base = base_c
+        else:
+            # host tensors (or fp32 weights): same arithmetic as diff.py:11-16, bits packed by the library's host codec
+            diff = finetune - base
+            quantile = diff.float().abs().mean()
+            mask = pack((~(diff < 0)).T)
+        self.register_buffer("mask", mask)
+        self.register_buffer("base", base.T)
+        self.register_parameter(
+            "coeff",
+            nn.Parameter(quantile.detach().clone().to(dtype=torch.float32, device=base.device).requires_grad_(True)),
+        )
+        self._w_cache = None
+
+    def _weight_nk(self) -> torch.Tensor:
+        """[N, K] row-major view of the base weight (zero-copy while ``base`` keeps the reference's (1, K) strides)."""
+        w = self.base.t()
+        if w.is_contiguous():
+            return w
+        key = (self.base.data_ptr(), self.base._version, self.base.device)
+        if self._w_cache is None or self._w_cache[0] != key:
+            self._w_cache = (key, w.contiguous())
+        return self._w_cache[1]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        # [B, seq, in] @ [in, out] + coeff * ([B, seq, in] @ sign[in, out])   (diff.py:33-39)
+        lead = x.shape[:-1]
+        rows = x.reshape(1, -1, x.shape[-1]).contiguous()
+        y = _fused_forward(rows, self._weight_nk(), self.mask, self.coeff, 1, self.kernel)
+        return y.reshape(*lead, y.shape[-1])
+
+
+def compress_diff(base_model, finetuned_model, finetuned_compressed_model):
+    """Swap every ``*proj`` child of modules named ``*mlp*``/``*self_attn*`` for a BinaryDiff (reference diff.py:41-64)."""
+
+    def compress_submodule(name, subname, module, submodule):
+        target_device = submodule.weight.device
+        base_weight = base_model.get_submodule(f"{name}.{subname}").weight.detach().to(target_device)
+        finetuned_weight = finetuned_model.get_submodule(f"{name}.{subname}").weight.detach().to(target_device)
+        compressed = BinaryDiff(base=base_weight, finetune=finetuned_weight).to(target_device)
+        del submodule, base_weight
+        setattr(module, subname, None)
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        setattr(module, subname, compressed)
+
+    for name, module in finetuned_compressed_model.named_modules():
+        if "mlp" in name or "self_attn" in name:
+            for subname, submodule in module.named_children():
+                if "proj" in subname:
+                    compress_submodule(name, subname, module, submodule)
+
+
+def save_diff(finetuned_compressed_model, save_dir):
+    """Write ``diff.pt``: ``<module>.mask`` int32 [K/32,N], ``<module>.coeff`` fp32 0-dim, then every trainable parameter
+    under its own name -- byte-compatible with reference diff.py:66-79."""
+    diff_dict = {}
+    for name, module in finetuned_compressed_model.named_modules():
+        if isinstance(module, BinaryDiff):
+            diff_dict[name + ".mask"] = module.mask.cpu()
+            diff_dict[name + ".coeff"] = module.coeff.cpu()
+    for name, param in finetuned_compressed_model.named_parameters():
+        if param.requires_grad:
+            diff_dict[name] = param.cpu()
+    torch.save(diff_dict, save_dir)
+
+
+@torch.no_grad()
+def load_diff(model, diff_dir):
+    """Fold a ``diff.pt`` into a dense model (reference diff.py:81-106): ``W += ((2*unpack(mask)-1)*coeff).T`` for
+    ``.mask`` entries (one device kernel, no [K,N] temporaries), replace ``.weight`` entries, add ``(A@B).T`` for LoRA pairs."""
+    device = model.device
+    diff_dict = torch.load(diff_dir, weights_only=False)
+    for name, module in model.named_modules():
+        if name + ".mask" in diff_dict:
+            coeff = diff_dict[name + ".coeff"].to(device)
+            mask = diff_dict[name + ".mask"].to(device)
+            fold_into(module.weight, mask, coeff)
+        elif name + ".weight" in diff_dict:
+            module.weight = nn.Parameter(diff_dict[name + ".weight"].to(device).to(module.weight.dtype))
+        elif name + ".A" in diff_dict:
+            A = diff_dict[name + ".A"].to(device)
+            B = diff_dict[name + ".B"].to(device)
+            module.weight.add_((A @ B).T.to(module.weight.dtype))
+    model.config.vocab_size = model.lm_head.weight.size(0)
+
+
+@torch.no_grad()
+def fold_into(weight: torch.Tensor, mask: torch.Tensor, coeff: torch.Tensor) -> None:
+    """In place ``weight[N,K] += round(((2*unpack(mask)-1) * coeff).T)`` in the weight dtype (diff.py:93-95)."""
+    N, K = weight.shape
+    assert mask.shape == (K // 32, N) and mask.dtype == torch.int32
+    if weight.is_cuda and weight.dtype in (torch.bfloat16, torch.float16) and weight.is_contiguous():
+        c = coeff.detach().to(device=weight.device, dtype=torch.float32).reshape(1).contiguous()
+        m = mask.to(weight.device).contiguous()
+        with torch.cuda.device(weight.device):
+            _lib.check(_lib.lib.bd_fold(weight.data_ptr(), m.data_ptr(), c.data_ptr(), _lib.dtype_code(weight.dtype), N, K,
+                                        _lib.stream_ptr(weight.device)))
+    else:
+        delta = (unpack(mask) * 2 - 1) * coeff
+        weight.add_(delta.T.to(weight.dtype))
+
+
+def save_full_model(base_model_name, finetuned_model_name, diff_dir, save_dir, device):
+    """Reference diff.py:108-116: load the base model, fold the diff, save model + tokenizer."""
+    import transformers
+
+    base_model = transformers.AutoModelForCausalLM.from_pretrained(
+        base_model_name, torch_dtype=torch.bfloat16, low_cpu_mem_usage=True
+    ).to(device)
+    tokenizer = transformers.AutoTokenizer.from_pretrained(finetuned_model_name)
+    load_diff(base_model, diff_dir)
+    base_model.save_pretrained(save_dir)
+    tokenizer.save_pretrained(save_dir)
+    del base_model

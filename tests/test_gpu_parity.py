@@ -1,0 +1,403 @@
+"""GPU parity tests: the CUDA path (through the Python surface -> ctypes -> C ABI) against the numpy oracle and the
+golden vectors produced by the reference.
+
+Tolerances (stated once, used everywhere):
+  * integer / bit work (pack, unpack, compress masks, fold): bit-exact.
+  * floating point: both products are accumulated in fp32 and the sum is rounded ONCE to the activation dtype, so against
+    the float64 truth every element must satisfy  |y - exact| <= (h + 1e-3) * |exact| + 1e-3 * mean|exact|
+    where h is the half-ulp relative rounding step of the output dtype (2^-9 for bf16, 2^-11 for fp16): 1e-3 relative for
+    the arithmetic (north_star), plus the unavoidable output quantisation, plus an absolute floor for cancelled sums.
+  * the notebook's own metric mean|y-ref| / mean|ref| (cells 22-24) must stay < 1e-3 for fp16 outputs and < 2e-3 for
+    bf16 outputs (one bf16 rounding alone is ~1.3e-3 by that metric).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bitdelta_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # keeps collection cheap on the CPU box; the marker deselects these anyway
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import bitdelta_b200 as bd  # noqa: E402
+
+DEV = torch.device("cuda:0")
+KERNELS = ["simt", "auto"]
+
+
+def bf(bits):
+    return O.bf16_bits_to_f32(bits)
+
+
+def t_bf16(bits: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16)
+
+
+def to_np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def assert_close_to_exact(y: torch.Tensor, exact: np.ndarray, what=""):
+    h = 2.0**-9 if y.dtype == torch.bfloat16 else 2.0**-11
+    got = to_np(y).astype(np.float64)
+    err = np.abs(got - exact)
+    bound = (h + 1e-3) * np.abs(exact) + 1e-3 * np.abs(exact).mean()
+    bad = err > bound
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} elements out of tolerance, worst {err.max():.4g}"
+    rel = O.rel_mean_abs_err(got, exact)
+    assert rel < (2e-3 if y.dtype == torch.bfloat16 else 1e-3), f"{what}: mean-rel {rel:.3g}"
+
+
+# ------------------------------------------------------------------------------------------------ codec
+@pytest.mark.parametrize("n_bits", [8, 16, 32, 64])
+def test_codec_matches_reference_vectors(golden, n_bits):
+    g = golden("codec.npz")
+    bits = torch.from_numpy(g["bits"]).to(DEV)
+    packed = bd.pack(bits, n_bits)
+    assert packed.device.type == "cuda" and np.array_equal(packed.cpu().numpy(), g[f"packed{n_bits}"])
+    assert torch.equal(bd.unpack(packed, n_bits), bits)
+
+
+def test_codec_known_answers_and_negative_words(golden):
+    g = golden("codec.npz")
+    assert np.array_equal(bd.pack(torch.from_numpy(g["kat_bits"]).to(DEV)).cpu().numpy(), g["kat_packed"])
+    words = torch.from_numpy(g["words"]).to(DEV)
+    assert np.array_equal(bd.unpack(words).cpu().numpy(), g["words_unpacked"])
+
+
+def test_codec_full_size_round_trip():
+    # Mistral-7B down_proj signs for 6 tenants: [6, 14336/32, 4096] words
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    words = torch.randint(-(2**31), 2**31 - 1, (6, 448, 4096), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    bits = bd.unpack(words)
+    assert bits.shape == (6, 14336, 4096) and bits.dtype == torch.bool
+    assert torch.equal(bd.pack(bits), words)
+    # popcount is preserved
+    w64 = words.to(torch.int64) & 0xFFFFFFFF
+    pop = sum(((w64 >> i) & 1).sum().item() for i in range(32))
+    assert pop == bits.sum().item()
+
+
+def test_codec_edge_cases():
+    assert bd.pack(torch.zeros(0, 32, 5, dtype=torch.bool, device=DEV)).shape == (0, 1, 5)
+    assert bd.unpack(torch.zeros(2, 0, 7, dtype=torch.int32, device=DEV)).shape == (2, 0, 7)
+    with pytest.raises(AssertionError, match="K must be divisible by n_bits"):
+        bd.pack(torch.zeros(33, 4, dtype=torch.bool, device=DEV))
+    # non-contiguous input (a transposed view, as BinaryDiff.__init__ passes it)
+    x = torch.rand(96, 64, device=DEV) > 0.5
+    assert np.array_equal(bd.pack(x.T).cpu().numpy(), O.pack(x.T.cpu().numpy()))
+
+
+# ------------------------------------------------------------------------------------------------ compress / fold
+def test_compress_matches_reference_ctor(golden):
+    g = golden("binarydiff_ctor.npz")
+    m = bd.BinaryDiff(t_bf16(g["base"]).to(DEV), t_bf16(g["finetune"]).to(DEV))
+    assert np.array_equal(m.mask.cpu().numpy(), g["mask"])
+    assert abs(m.coeff.item() - float(g["coeff"])) <= 1e-6 * float(g["coeff"])
+    assert list(m.state_dict().keys()) == list(g["state_keys"])
+    assert m.base.shape == (96, 48) and m.base.stride() == (1, 96)
+    assert m.coeff.dtype == torch.float32 and m.coeff.dim() == 0 and m.coeff.requires_grad
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_compress_full_size_properties(dtype):
+    torch.manual_seed(0)
+    N, K = 4096, 4096
+    base = (torch.randn(N, K, device=DEV) * 0.02).to(dtype)
+    fine = (base.float() + torch.randn(N, K, device=DEV) * 0.002).to(dtype)
+    fine[5, :100] = base[5, :100]
+    m = bd.BinaryDiff(base, fine)
+    diff = fine - base
+    want_bits = ~(diff < 0)
+    assert torch.equal(bd.unpack(m.mask), want_bits.T)
+    want_coeff = diff.double().abs().mean().item()
+    assert abs(m.coeff.item() - want_coeff) <= 1e-6 * want_coeff
+    # against the oracle on a slab
+    mask_o, coeff_o = O.binarydiff_compress(to_np(base[:64]), to_np(fine[:64]))
+    assert np.array_equal(m.mask[:, :64].cpu().numpy(), mask_o)
+
+
+def test_fold_matches_load_diff(golden):
+    g = golden("tiny_llama.npz")
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt"), weights_only=False)
+    for name in ["model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.layers.1.self_attn.k_proj"]:
+        w = t_bf16(g["base::" + name]).to(DEV).clone()
+        bd.fold_into(w, d[name + ".mask"].to(DEV), d[name + ".coeff"])
+        got = w.cpu().view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got, g["folded::" + name]), name
+
+
+# ------------------------------------------------------------------------------------------------ binary_matmul / binary_bmm
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_notebook_cell7_binary_matmul(kernel):
+    # notebook cell 7: seed 0, a = randn(512,512) fp16, b = randn(512,512) > 0.5, allclose(atol=1e-2, rtol=0)
+    torch.manual_seed(0)
+    a = torch.randn((512, 512), device=DEV, dtype=torch.float16)
+    b = torch.randn((512, 512), device=DEV) > 0.5
+    c = bd.binary_matmul(a, bd.pack(b), kernel=kernel)
+    ref = torch.matmul(a.float(), b.float() * 2 - 1)
+    # fp16 output spacing at |c| ~ 64 is 0.03-0.06, so the notebook's atol=1e-2 only holds between two fp16 results;
+    # against the fp32 product we allow half an fp16 ulp on top of it.
+    assert torch.allclose(c.float(), ref, atol=1e-2 + 0.5 * 2.0**-4, rtol=0)
+    assert_close_to_exact(c, O.binary_matmul_exact(to_np(a), bd.pack(b).cpu().numpy()), "cell7")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_notebook_cell13_binary_bmm(kernel, dtype):
+    # notebook cells 13-14: a = randn(16,128,512), b = randn(16,512,1024) > 0.5, allclose(rtol=1e-2); recorded max rel 0.0062
+    torch.manual_seed(0)
+    a = torch.randn((16, 128, 512), device=DEV, dtype=dtype)
+    b = torch.randn((16, 512, 1024), device=DEV) > 0.5
+    words = bd.pack(b)
+    c = bd.binary_bmm(a, words, kernel=kernel)
+    assert c.shape == (16, 128, 1024) and c.dtype == dtype
+    assert_close_to_exact(c, O.binary_bmm_exact(to_np(a), words.cpu().numpy()), "cell13")
+
+
+def test_binary_bmm_matches_triton_interpreter_vectors(golden):
+    g = golden("triton_interp.npz")
+    a3 = torch.from_numpy(g["a3"]).to(DEV)
+    c3 = bd.binary_bmm(a3, torch.from_numpy(g["b3"]).to(DEV))
+    # the reference kernel rounds fp32 -> fp16 once for fp16 inputs, as we do: results agree to the last fp16 bit up to
+    # fp32 summation order
+    diff = (c3.float().cpu() - torch.from_numpy(g["c3"]).float()).abs()
+    assert (diff <= 2.0**-10 * torch.from_numpy(g["c3"]).float().abs() + 1e-3).all()
+    c2 = bd.binary_matmul(torch.from_numpy(g["a"]).to(DEV), torch.from_numpy(g["b"]).to(DEV))
+    assert O.rel_mean_abs_err(to_np(c2), g["c"].astype(np.float32)) < 2e-4
+
+
+def test_binary_bmm_assertions():
+    a = torch.zeros(2, 4, 64, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(2, 2, 8, device=DEV, dtype=torch.int32)
+    with pytest.raises(AssertionError, match="Matrix A must be 3D"):
+        bd.binary_bmm(a[0], b)
+    with pytest.raises(AssertionError, match="Incompatible dimensions"):
+        bd.binary_bmm(a[:, :, :32], b)
+    with pytest.raises(AssertionError, match="Incompatible batch dimensions"):
+        bd.binary_bmm(a, b[:1])
+    with pytest.raises(AssertionError, match="Matrix A must be contiguous"):
+        bd.binary_bmm(a.transpose(0, 1).contiguous().transpose(0, 1), b)
+    with pytest.raises(AssertionError, match="same device"):
+        bd.binary_bmm(a, b.cpu())
+    assert bd.binary_bmm(a[:, :0], b).shape == (2, 0, 8)
+
+
+# ------------------------------------------------------------------------------------------------ BinaryDiff.forward
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_binarydiff_forward_reference_vectors(golden, kernel):
+    g = golden("binarydiff_forward.npz")
+    m = bd.BinaryDiff(t_bf16(g["base"]).to(DEV), t_bf16(g["finetune"]).to(DEV))
+    m.kernel = kernel
+    assert np.array_equal(m.mask.cpu().numpy(), g["mask"])
+    x = t_bf16(g["x"]).to(DEV)
+    y = m(x)
+    assert y.shape == (2, 5, 160) and y.dtype == torch.bfloat16
+    exact = O.binarydiff_forward_exact(bf(g["x"]), bf(g["base"]), g["mask"], g["coeff"])
+    assert_close_to_exact(y, exact, "golden forward")
+    # the reference's own CPU evaluations of diff.py:39
+    assert O.rel_mean_abs_err(to_np(y), g["y_f32"]) < 2e-3
+    assert O.rel_mean_abs_err(to_np(y), bf(g["y_bf16"])) < 4e-3
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("M", [1, 16, 128])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_config1_single_4096_linear(kernel, M, dtype):
+    # BASELINE config 1 / SURVEY 8d: seed 0, W_base = randn*0.02, W_fine = W_base + randn*0.002, x = randn(1, M, 4096)
+    torch.manual_seed(0)
+    base = (torch.randn(4096, 4096) * 0.02).to(dtype)
+    fine = (base.float() + torch.randn(4096, 4096) * 0.002).to(dtype)
+    x = torch.randn(1, M, 4096).to(dtype)
+    m = bd.BinaryDiff(base.to(DEV), fine.to(DEV))
+    m.kernel = kernel
+    y = m(x.to(DEV))
+    mask = m.mask.cpu().numpy()
+    mask_o, coeff_o = O.binarydiff_compress(to_np(base), to_np(fine))
+    assert np.array_equal(mask, mask_o)
+    assert np.array_equal(bd.unpack(m.mask).cpu().numpy(), O.unpack(mask_o))  # bit-exact int32 unpack
+    exact = O.binarydiff_forward_exact(to_np(x), to_np(base), mask, m.coeff.item())
+    assert_close_to_exact(y, exact, f"config1 M={M}")
+    if dtype == torch.bfloat16:
+        emu = O.binarydiff_forward(to_np(x), to_np(base), mask, m.coeff.item())
+        assert O.rel_mean_abs_err(to_np(y), emu) < 4e-3
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("N,K,rows", [(50, 32, 3), (64, 64, 1), (200, 96, 9), (1024, 4096, 6), (72, 2080, 17)])
+def test_forward_ragged_shapes(kernel, N, K, rows):
+    torch.manual_seed(N + K + rows)
+    base = (torch.randn(N, K) * 0.05).bfloat16()
+    fine = (base.float() + torch.randn(N, K) * 0.01).bfloat16()
+    x = torch.randn(rows, K).bfloat16()
+    m = bd.BinaryDiff(base.to(DEV), fine.to(DEV))
+    m.kernel = kernel
+    y = m(x.to(DEV))
+    exact = O.binarydiff_forward_exact(to_np(x), to_np(base), m.mask.cpu().numpy(), m.coeff.item())
+    assert_close_to_exact(y, exact, f"ragged {N}x{K}x{rows}")
+
+
+def test_forward_is_deterministic_and_workspace_is_left_clean():
+    torch.manual_seed(1)
+    base = (torch.randn(1024, 4096, device=DEV) * 0.02).bfloat16()
+    fine = (base.float() + torch.randn_like(base.float()) * 0.002).bfloat16()
+    m = bd.BinaryDiff(base, fine)
+    m.kernel = "simt"
+    x = torch.randn(1, 6, 4096, device=DEV).bfloat16()
+    y0 = m(x)
+    for _ in range(5):
+        assert torch.equal(m(x), y0)
+
+
+# ------------------------------------------------------------------------------------------------ multi-tenant modules
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_diffcompress_reference_vectors(golden, kernel):
+    g = golden("demo_modules.npz")
+    lin = torch.nn.Linear(128, 96, bias=False).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(t_bf16(g["weight"]).to(DEV))
+    mod = bd.DiffCompressModule(lin, torch.from_numpy(g["masks"]).to(DEV), t_bf16(g["coeffs"]).to(DEV))
+    mod.kernel = kernel
+    y = mod(t_bf16(g["x"]).to(DEV))
+    exact = O.diffcompress_forward_exact(bf(g["x"]), bf(g["weight"]), g["masks"], bf(g["coeffs"]))
+    assert_close_to_exact(y, exact, "DiffCompressModule golden")
+    assert O.rel_mean_abs_err(to_np(y), bf(g["y"])) < 4e-3  # vs the reference module's bf16 output
+
+
+def test_dataparallel_reference_vectors(golden):
+    g = golden("demo_modules.npz")
+    x = t_bf16(g["x"]).to(DEV)
+    head = torch.nn.Linear(128, 50, bias=False).to(DEV, torch.bfloat16)
+    ws = [t_bf16(g[f"head_w{i}"]).to(DEV) for i in range(3)]
+    logits = bd.DataParallelModule(head, ws)(x)
+    ref = bf(g["logits"])
+    assert logits.shape == (3, 2, 52)
+    assert torch.all(logits[0, :, 50:] == torch.finfo(torch.bfloat16).min)
+    assert O.rel_mean_abs_err(to_np(logits)[:, :, :50], ref[:, :, :50]) < 2e-3
+    assert O.rel_mean_abs_err(to_np(logits)[1:], ref[1:]) < 2e-3
+    emb = torch.nn.Embedding(52, 128).to(DEV, torch.bfloat16)
+    out = bd.DataParallelModule(emb, [t_bf16(e).to(DEV) for e in g["emb_w"]])(torch.from_numpy(g["ids"]).to(DEV))
+    assert np.array_equal(to_np(out), bf(g["emb_out"]))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("N,K,m", [(1024, 4096, 1), (4096, 14336, 1), (4096, 4096, 3)])
+def test_mistral_shapes_six_tenants(kernel, N, K, m):
+    # BASELINE config 3 shapes (k_proj, down_proj, q_proj), T = 6 tenants, decode rows
+    T = 6
+    gen = torch.Generator(device=DEV).manual_seed(N + K + m)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.003 + 0.0005).bfloat16()
+    x = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    mod.kernel = kernel
+    y = mod(x)
+    # float64 truth on the GPU from the bit-exact unpack (checked against the oracle on a slab below)
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact = x.double() @ w.double().T + coeffs.double()[:, None, None] * torch.bmm(x.double(), signs)
+    assert_close_to_exact(y, exact.cpu().numpy(), f"mistral {N}x{K}")
+    sl = slice(0, 96)
+    ex_o = O.diffcompress_forward_exact(to_np(x), to_np(w[sl]), masks[:, :, sl].cpu().numpy(), to_np(coeffs))
+    assert np.allclose(exact[:, :, sl].cpu().numpy(), ex_o, rtol=1e-9, atol=1e-9)
+
+
+def test_linearity_in_the_coefficient():
+    # size-independent property at full size: y(2c) - y(c) == y(c) - y(0)  up to bf16 rounding
+    T, N, K = 6, 4096, 4096
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    x = torch.randn(T, 1, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    c = torch.full((T,), 0.002, device=DEV)
+    y0 = bd.DiffCompressModule(lin, masks, c * 0)(x).float()
+    y1 = bd.DiffCompressModule(lin, masks, c)(x).float()
+    y2 = bd.DiffCompressModule(lin, masks, c * 2)(x).float()
+    base_only = (x.float() @ w.float().T)
+    assert O.rel_mean_abs_err(to_np(y0), to_np(base_only)) < 2e-3
+    d1, d2 = (y1 - y0), (y2 - y1)
+    delta = 0.002 * torch.bmm(x.float(), bd.unpack(masks).float() * 2 - 1)
+    assert (d1 - delta).abs().mean() / delta.abs().mean() < 0.1  # differences of bf16-rounded outputs: coarse
+    assert (d2 - delta).abs().mean() / delta.abs().mean() < 0.1
+
+
+def test_register_and_unregister_diff_compress():
+    import torch.nn as nn
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = nn.Linear(64, 96, bias=False)
+            self.norm = nn.LayerNorm(64, bias=False)
+
+        def forward(self, x):
+            return self.q_proj(self.norm(x))
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.block = Block()
+
+        def forward(self, x):
+            return self.block(x)
+
+    torch.manual_seed(0)
+    model = Model().to(DEV, torch.bfloat16)
+    T = 3
+    ckpts = []
+    for _ in range(T):
+        ckpts.append({
+            "block.q_proj.mask": bd.pack(torch.rand(64, 96, device=DEV) > 0.5),
+            "block.q_proj.coeff": torch.tensor(0.01, device=DEV),
+            "block.norm.weight": torch.rand(64, device=DEV).bfloat16(),
+        })
+    ref_ckpts = [dict(c) for c in ckpts]
+    bd.demo_backend.cached_modules.clear()
+    x = torch.randn(T, 4, 64, device=DEV).bfloat16()
+    with bd.DiffCompress(model, ckpts):
+        assert isinstance(model.block.q_proj, bd.DiffCompressModule)
+        assert isinstance(model.block.norm, bd.DataParallelModule)
+        assert model.block.q_proj.mask.shape == (T, 2, 96)
+        assert "block.q_proj.mask" not in ckpts[0]  # popped like the reference does
+        y = model(x)
+    assert isinstance(model.block.q_proj, nn.Linear) and isinstance(model.block.norm, nn.LayerNorm)
+    for t in range(T):
+        h = torch.nn.functional.layer_norm(x[t].float(), (64,), ref_ckpts[t]["block.norm.weight"].float()).bfloat16()
+        signs = bd.unpack(ref_ckpts[t]["block.q_proj.mask"]).double() * 2 - 1
+        exact = h.double() @ model.block.q_proj.weight.double().T + 0.01 * (h.double() @ signs)
+        assert_close_to_exact(y[t], exact.cpu().numpy(), f"tenant {t}")
+    bd.demo_backend.cached_modules.clear()
+
+
+def test_cuda_graph_capture_of_the_fused_forward():
+    T, N, K = 6, 1024, 4096
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = torch.full((T,), 0.002, device=DEV)
+    x = torch.randn(T, 1, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y_eager = mod(x)  # warm-up on the capture stream (allocates its workspace)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            y_graph = mod(x)
+        graph.replay()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_graph, y_eager)

@@ -1,0 +1,168 @@
+"""Host-side behaviour of the reference-compatible Python surface (no GPU needed)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bitdelta_b200 as bd
+from oracle import bitdelta_oracle as O
+
+
+def t_bf16(bits):
+    return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16)
+
+
+def test_reference_names_and_signatures():
+    import inspect
+
+    assert list(inspect.signature(bd.pack).parameters) == ["x", "n_bits"]
+    assert list(inspect.signature(bd.unpack).parameters) == ["x", "n_bits"]
+    assert list(inspect.signature(bd.binary_matmul).parameters)[:4] == ["a", "b", "n_bits", "activation"]
+    assert list(inspect.signature(bd.binary_bmm).parameters)[:4] == ["a", "b", "n_bits", "activation"]
+    assert list(inspect.signature(bd.BinaryDiff.__init__).parameters) == ["self", "base", "finetune"]
+    assert list(inspect.signature(bd.DiffCompressModule.__init__).parameters) == ["self", "module", "mask_list", "coeff_list"]
+    assert list(inspect.signature(bd.DataParallelModule.__init__).parameters) == ["self", "module", "weight_list"]
+    assert list(inspect.signature(bd.register_diff_compress).parameters) == ["model", "checkpoint_list"]
+    for name in ["compress_diff", "save_diff", "load_diff", "save_full_model", "unregister_diff_compress", "DiffCompress"]:
+        assert hasattr(bd, name)
+
+
+@pytest.mark.parametrize("n_bits", [8, 16, 32, 64])
+def test_host_codec_matches_reference_vectors(golden, n_bits):
+    g = golden("codec.npz")
+    bits = torch.from_numpy(g["bits"])
+    packed = bd.pack(bits, n_bits)
+    assert packed.dtype == {8: torch.uint8, 16: torch.int16, 32: torch.int32, 64: torch.int64}[n_bits]
+    assert np.array_equal(packed.numpy(), g[f"packed{n_bits}"])
+    assert torch.equal(bd.unpack(packed, n_bits), bits)
+
+
+def test_host_codec_fuzz_against_oracle():
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        lead = tuple(rng.integers(1, 3, size=rng.integers(0, 3)))
+        J, N = int(rng.integers(1, 5)), int(rng.integers(1, 70))
+        bits = rng.random(lead + (J * 32, N)) > rng.random()
+        packed = bd.pack(torch.from_numpy(bits))
+        assert np.array_equal(packed.numpy(), O.pack(bits))
+        assert np.array_equal(bd.unpack(packed).numpy(), bits)
+
+
+def test_pack_assertion_and_transposed_input():
+    with pytest.raises(AssertionError, match="K must be divisible by n_bits"):
+        bd.pack(torch.zeros(33, 4, dtype=torch.bool))
+    x = torch.rand(96, 64) > 0.5
+    assert np.array_equal(bd.pack(x.T).numpy(), O.pack(x.T.numpy()))
+    assert bd.pack(torch.zeros(0, 32, 5, dtype=torch.bool)).shape == (0, 1, 5)
+
+
+def test_gemm_refuses_cpu_tensors_loudly():
+    a = torch.zeros(1, 1, 32, dtype=torch.bfloat16)
+    b = torch.zeros(1, 1, 4, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bd.binary_bmm(a, b)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bd.binary_matmul(a[0], b[0])
+    m = bd.BinaryDiff(torch.zeros(8, 32, dtype=torch.bfloat16), torch.ones(8, 32, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 32, dtype=torch.bfloat16))
+    with pytest.raises(AssertionError, match="Matrix A must be 3D"):
+        bd.binary_bmm(a[0], b)
+    with pytest.raises(AssertionError, match="Incompatible dimensions"):
+        bd.binary_bmm(torch.zeros(1, 1, 64, dtype=torch.bfloat16), b)
+
+
+def test_binarydiff_ctor_on_host_matches_reference(golden):
+    g = golden("binarydiff_ctor.npz")
+    m = bd.BinaryDiff(t_bf16(g["base"]), t_bf16(g["finetune"]))
+    assert np.array_equal(m.mask.numpy(), g["mask"])
+    assert abs(m.coeff.item() - float(g["coeff"])) <= 1e-6 * float(g["coeff"])
+    assert list(m.state_dict().keys()) == list(g["state_keys"])
+    assert m.base.stride() == (1, 96) and m.coeff.requires_grad and m.coeff.dtype == torch.float32
+
+
+def _tiny_models(golden):
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    g = golden("tiny_llama.npz")
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=96, max_position_embeddings=64, tie_word_embeddings=False)
+    sd = {}
+    for k in g.files:
+        if k.startswith("basesd::"):
+            v = g[k]
+            sd[k[len("basesd::"):]] = t_bf16(v) if v.dtype == np.uint16 else torch.from_numpy(v)
+    base = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    base.load_state_dict(sd)
+    return g, cfg, base
+
+
+def test_diff_pt_round_trip_against_reference_file(golden, tmp_path):
+    """compress_diff + save_diff write the same dict the reference wrote; load_diff folds it to the same weights."""
+    from transformers import LlamaForCausalLM
+
+    g, cfg, base = _tiny_models(golden)
+    ref = torch.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt"), weights_only=False)
+    # rebuild the fine-tuned model from the reference diff: full leaves from the file, projections from base + stored fine slabs
+    fine = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    fine.load_state_dict(base.state_dict())
+    folded = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    folded.load_state_dict(base.state_dict())
+    bd.load_diff(folded, os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt"))
+    for name in ["model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.layers.1.self_attn.k_proj"]:
+        got = folded.get_submodule(name).weight.detach().view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got, g["folded::" + name]), name
+    assert np.array_equal(folded.lm_head.weight.detach().view(torch.int16).numpy().view(np.uint16), g["folded::lm_head"])
+    ids = torch.from_numpy(g["ids"])
+    with torch.no_grad():
+        logits = folded(ids).logits.float().numpy()
+    assert np.allclose(logits, g["folded_logits"], rtol=0, atol=1e-6)
+
+    # now the writer: compress a model whose projections carry the reference's fine weights where we have them
+    with torch.no_grad():
+        for name in ["model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.layers.1.self_attn.k_proj"]:
+            fine.get_submodule(name).weight.copy_(t_bf16(g["fine::" + name]))
+    comp = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    comp.load_state_dict(fine.state_dict())
+    bd.compress_diff(base, fine, comp)
+    out = tmp_path / "diff.pt"
+    bd.save_diff(comp, str(out))
+    mine = torch.load(str(out), weights_only=False)
+    assert list(mine.keys()) == list(ref.keys())
+    for k in ref:
+        assert mine[k].dtype == ref[k].dtype and mine[k].shape == ref[k].shape, k
+    for name in ["model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj", "model.layers.1.self_attn.k_proj"]:
+        assert torch.equal(mine[name + ".mask"], ref[name + ".mask"])
+        assert abs(mine[name + ".coeff"].item() - ref[name + ".coeff"].item()) <= 1e-6 * ref[name + ".coeff"].item()
+
+
+def test_register_unregister_on_host_modules():
+    import torch.nn as nn
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = nn.Linear(64, 32, bias=False)
+            self.norm = nn.LayerNorm(64, bias=False)
+
+    model = M()
+    orig_w = model.norm.weight.data
+    ckpts = [{"q_proj.mask": bd.pack(torch.rand(64, 32) > 0.5), "q_proj.coeff": torch.tensor(0.1 * (i + 1)),
+              "norm.weight": torch.full((64,), float(i))} for i in range(2)]
+    bd.demo_backend.cached_modules.clear()
+    bd.register_diff_compress(model, ckpts)
+    assert isinstance(model.q_proj, bd.DiffCompressModule) and isinstance(model.norm, bd.DataParallelModule)
+    assert model.q_proj.mask.shape == (2, 2, 32) and model.q_proj.coeff.shape == (2,)
+    assert "q_proj.mask" not in ckpts[0] and "norm.weight" in ckpts[0]
+    out = model.norm(torch.ones(2, 3, 64) * torch.arange(64))
+    assert out.shape == (2, 3, 64) and torch.all(out[0] == 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.q_proj(torch.zeros(2, 1, 64))
+    bd.unregister_diff_compress(model)
+    assert isinstance(model.q_proj, nn.Linear) and isinstance(model.norm, nn.LayerNorm)
+    assert model.norm.weight.data.data_ptr() == orig_w.data_ptr()
+    bd.demo_backend.cached_modules.clear()
+    with pytest.raises(AssertionError, match="Only support linear layer"):
+        bd.register_diff_compress(M(), [{"norm.mask": torch.zeros(2, 64, dtype=torch.int32), "norm.coeff": torch.tensor(1.0)}])
+    bd.demo_backend.cached_modules.clear()
