@@ -1,7 +1,629 @@
-// tcgen05 / TMEM / TMA forward kernel (placeholder until the kernel lands; everything routes to the SIMT kernel).
+// tcgen05 / TMEM / TMA fused forward kernel for sm_100a.
+//
+//   y[t,i,n] = sum_k x[t,i,k] w[n,k]  +  coeff[t] * sum_k x[t,i,k] s_t[k,n]          s_t = 2*unpack(masks[t]) - 1
+//
+// replaces BinaryDiff.forward (bitdelta/diff.py:33-39), DiffCompressModule.forward (demo/demo_backend.py:93-98) and,
+// without the base term, binary_bmm (bitdelta/binary_gemm_kernel.py:297-335).
+//
+// Design (swap-AB, weights on MMA-M = 128, tokens on MMA-N):
+//   * work unit = (128-row tile of N, 64-wide block of K); units are dealt to a persistent grid of one CTA per SM in
+//     contiguous runs (stream-K), so every SM streams the same number of weight bytes whatever the layer shape.
+//   * warp 0 (producer): per unit, three TMA loads into one pipeline stage: the bf16 W tile [128 x 64] (SWIZZLE_128B,
+//     K-major, exactly how nn.Linear.weight sits in memory), the sign words [T x 2 x 128] int32 (the natural
+//     [K/32, N] pack layout: one 512-byte run per (tenant, 32-K group)), and the activation block [rows x 64].
+//   * warps 2-9 (unpack): thread <-> weight row (= TMEM lane).  A thread reads its row's sign word from shared memory
+//     (conflict-free), turns the 32 bits into 16 packed +-1.0 pairs with one shift + one LOP3 per pair
+//     (bit i -> low half, bit i+16 -> high half of register i, sign = ~bit) and writes them straight into TENSOR
+//     MEMORY with tcgen05.st: the unpacked sign tile is the A operand of a tcgen05.mma read from TMEM, it never
+//     touches shared memory.  The K order inside each 32-group is therefore (0,16,1,17,...); the same warps build
+//     the matching K-permuted copy of each tenant's activation rows (a few hundred bytes) as the B operand.
+//   * warp 1 (MMA issuer, one thread): per unit 4 MMAs  D_base += W_tile . X^T  (A and B from shared memory) and
+//     4 per tenant  D_delta[:, cols(t)] += S_t . X_t^T  (A from TMEM).  Two fp32 accumulators in TMEM so that the
+//     per-tenant coefficient is applied exactly, in fp32, in the epilogue (the reference's "TODO: Fuse coeff").
+//   * epilogue (warps 2-9 after the last unit of a tile run): tcgen05.ld, y = base + coeff * delta, one rounding.
+//     A run that covers only part of K writes fp32 partials to a per-CTA slot; the last CTA to finish a tile sums
+//     the slots in K order (deterministic) and stores y.
+//
+// HBM-bound by construction at decode sizes (algorithmic bytes per unit: 16 KiB of W + T KiB of signs); the binding
+// on-chip resource is the integer pipe doing the unpack, which is why it is kept to two ALU ops per two elements.
+#include <cuda.h>
+
+#include <mutex>
+#include <type_traits>
+
 #include "bd_common.cuh"
+
 namespace bd {
-bool umma_supports(const FwdProblem&, const char** why) { *why = "tcgen05 kernel not built yet"; return false; }
-int launch_fwd_umma(const FwdProblem&) { return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel not built yet"); }
-size_t umma_workspace_bytes(int64_t, int64_t) { return 0; }
+namespace {
+
+constexpr int kTileN = 128;   // weight rows per tile (MMA M)
+constexpr int kBlockK = 64;   // K per unit (one 128-byte swizzle atom of bf16)
+constexpr int kNumABuf = 2;   // TMEM A-operand buffers
+constexpr int kUnpackWarps = 8;
+constexpr int kThreads = 32 * (2 + kUnpackWarps);
+constexpr int kMaxStages = 8;
+constexpr int kMaxRows = 128;  // rows (tokens) per launch
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// ---------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 in bits [46,48), layout type 2 in
+// bits [61,64)); rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, K-major A and B, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 = f16, 1 = bf16*/, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------- kernel
+struct UmmaArgs {
+  const void* coeff;
+  int coeff_dtype;
+  void* y;
+  float* partial;     // [grid][2][rows][128]
+  unsigned* counters; // [n_tiles]
+  int T, m, rows;     // tenants, rows per tenant, T*m
+  int mp;             // rows per tenant padded to 16 (delta accumulator columns per tenant)
+  int ntb;            // T*m padded to 16 (base accumulator columns)
+  int K, N;
+  int kblocks;        // ceil(K / 64)
+  int n_tiles;
+  int total_units, units_per_cta, units_rem;  // CTA c owns units [c*U + min(c,R), ...)
+  int stages;
+  uint32_t stage_bytes, off_masks, off_x;     // stage layout: [W tile][masks][X tile]
+  uint32_t off_xp, xp_buf_bytes;              // permuted activation tiles, one per A buffer
+  uint32_t tx_bytes;
+};
+
+__device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return c * a.units_per_cta + min(c, a.units_rem); }
+
+template <typename T16, bool HAS_BASE>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_m,
+                const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles and their UMMA descriptors need 1024-byte alignment: align by hand (the host adds 1 KiB of slack)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_afull[kNumABuf], bar_aempty[kNumABuf], bar_dfull;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ unsigned s_is_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int u_begin = cta_unit_begin(a, cta), u_end = cta_unit_begin(a, cta + 1);
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    if (HAS_BASE) prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_m);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1 + kUnpackWarps);
+    }
+    for (int b = 0; b < kNumABuf; ++b) {
+      mbar_init(&bar_afull[b], kUnpackWarps);
+      mbar_init(&bar_aempty[b], 1);
+    }
+    mbar_init(&bar_dfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kTmemCols);
+  // zero the permuted-activation tiles once: rows >= m of every tenant tile stay zero for the whole kernel
+  for (uint32_t i = threadIdx.x * 16; i < kNumABuf * a.xp_buf_bytes; i += kThreads * 16)
+    *reinterpret_cast<uint4*>(smem + a.off_xp + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  // TMEM columns: [0, ntb) base accumulator, [ntb, ntb + T*mp) delta accumulator, then the A-operand buffers
+  const uint32_t col_dbase = 0, col_ddelta = a.ntb;
+  const uint32_t a_cols_per_buf = (uint32_t)a.T * (kBlockK / 2);
+  const uint32_t col_abuf0 = kTmemCols - kNumABuf * a_cols_per_buf;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int u = u_begin; u < u_end; ++u, ++it) {
+        const int s = it % a.stages;
+        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+        const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
+        mbar_wait(&bar_empty[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * a.stage_bytes;
+        mbar_arrive_expect_tx(&bar_full[s], a.tx_bytes);
+        if (HAS_BASE) tma_load_2d(st, &tmap_w, &bar_full[s], kb * kBlockK, tile * kTileN, kEvictFirst);
+        tma_load_3d(st + a.off_masks, &tmap_m, &bar_full[s], tile * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
+        tma_load_2d(st + a.off_x, &tmap_x, &bar_full[s], kb * kBlockK, 0, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr int fmt = std::is_same<T16, __nv_bfloat16>::value ? 1 : 0;
+    const uint32_t idesc_base = make_idesc(fmt, a.ntb);
+    const uint32_t idesc_delta = make_idesc(fmt, a.mp);
+    int it = 0;
+    uint32_t dphase = 0;
+    (void)dphase;
+    for (int u = u_begin; u < u_end; ++u, ++it) {
+      const int s = it % a.stages, b = it % kNumABuf;
+      const uint32_t ph = (uint32_t)(it / a.stages) & 1u, aph = (uint32_t)(it / kNumABuf) & 1u;
+      const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
+      const bool seg_first = (u == u_begin) || (kb == 0);
+      const bool seg_last = (u + 1 == u_end) || (kb + 1 == a.kblocks);
+      mbar_wait(&bar_full[s], ph);
+      mbar_wait(&bar_afull[b], aph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * a.stage_bytes);
+        const uint32_t xp = smem_u32(smem + a.off_xp + (size_t)b * a.xp_buf_bytes);
+#pragma unroll
+        for (int ks = 0; ks < kBlockK / 16; ++ks) {
+          const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
+          if (HAS_BASE)
+            mma_ss(tmem_base + col_dbase, smem_desc_sw128(st + ks * 32), smem_desc_sw128(st + a.off_x + ks * 32), idesc_base, acc);
+        }
+        for (int t = 0; t < a.T; ++t) {
+#pragma unroll
+          for (int ks = 0; ks < kBlockK / 16; ++ks) {
+            const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
+            mma_ts(tmem_base + col_ddelta + t * a.mp, tmem_base + col_abuf0 + b * a_cols_per_buf + t * (kBlockK / 2) + ks * 8,
+                   smem_desc_sw128(xp + t * a.mp * 128 + ks * 32), idesc_delta, acc);
+          }
+        }
+        tc_commit(&bar_empty[s]);   // stage (W tile, X tile) may be overwritten once these MMAs retire
+        tc_commit(&bar_aempty[b]);  // so may the TMEM A buffer and its permuted-X tiles
+        if (seg_last) tc_commit(&bar_dfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== unpack + epilogue warps
+    const int uw = warp - 2;            // 0..7
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
+    const int grp = uw >> 2;            // two warps per quadrant: they split the tenants
+    const int row = quad * 32 + lane;   // weight row inside the tile == TMEM lane
+    const int ut = threadIdx.x - 64;    // 0..255
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    constexpr uint32_t kOne = std::is_same<T16, __nv_bfloat16>::value ? 0x3F803F80u : 0x3C003C00u;
+    T16* __restrict__ y = reinterpret_cast<T16*>(a.y);
+    uint32_t sign_mask = 0x80008000u;
+    asm volatile("" : "+r"(sign_mask));  // keep the mask in a register so mask + constant fit one LOP3
+    int it = 0, seg_u0 = u_begin;
+    uint32_t dphase = 0;
+    for (int u = u_begin; u < u_end; ++u, ++it) {
+      const int s = it % a.stages, b = it % kNumABuf;
+      const uint32_t ph = (uint32_t)(it / a.stages) & 1u, aph = (uint32_t)(it / kNumABuf) & 1u;
+      const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
+      if (kb == 0) seg_u0 = u;  // a new (tile, K run) starts here (or at u_begin)
+      const bool seg_last = (u + 1 == u_end) || (kb + 1 == a.kblocks);
+      mbar_wait(&bar_full[s], ph);
+      mbar_wait(&bar_aempty[b], aph ^ 1u);
+      tc_fence_after();
+      const uint8_t* st = smem + (size_t)s * a.stage_bytes;
+
+      // (1) K-permuted copy of every tenant's activation rows: out chunk c of a 32-group = x[4c..4c+3] interleaved with
+      //     x[4c+16..4c+19]; both tiles use the 128-byte swizzle (16-byte chunk index XOR row % 8).
+      {
+        uint8_t* xp = smem + a.off_xp + (size_t)b * a.xp_buf_bytes;
+        const int jobs = a.rows * 8;
+        for (int job = ut; job < jobs; job += kUnpackWarps * 32) {
+          const int r = job >> 3, c = job & 7;          // r = global row, c = output chunk (0..7) of the 64-K block
+          const int g = c >> 2, cc = c & 3;             // 32-group, chunk inside the group
+          const int ca = 4 * g + (cc >> 1), cb = ca + 2;  // source chunks holding x[4cc..] and x[4cc+16..]
+          const uint8_t* src = st + a.off_x + r * 128;
+          const uint2 va = *reinterpret_cast<const uint2*>(src + ((ca ^ (r & 7)) << 4) + ((cc & 1) << 3));
+          const uint2 vb = *reinterpret_cast<const uint2*>(src + ((cb ^ (r & 7)) << 4) + ((cc & 1) << 3));
+          uint4 o;
+          o.x = __byte_perm(va.x, vb.x, 0x5410);  // (a0, b0)
+          o.y = __byte_perm(va.x, vb.x, 0x7632);  // (a1, b1)
+          o.z = __byte_perm(va.y, vb.y, 0x5410);  // (a2, b2)
+          o.w = __byte_perm(va.y, vb.y, 0x7632);  // (a3, b3)
+          const int t = r / a.m, i = r - t * a.m;
+          *reinterpret_cast<uint4*>(xp + (t * a.mp + i) * 128 + ((c ^ (i & 7)) << 4)) = o;
+        }
+      }
+
+      // (2) sign words -> +-1.0 pairs -> TMEM A operand
+      {
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(st + a.off_masks);
+        for (int t = grp; t < a.T; t += 2) {
+#pragma unroll
+          for (int jj = 0; jj < kBlockK / 32; ++jj) {
+            const uint32_t w = mw[(t * (kBlockK / 32) + jj) * kTileN + row];
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t sh = w << (15 - i);                 // bit i -> 15, bit i+16 -> 31
+              // r = (~sh & 0x80008000) | one : sign = ~bit, bit 1 -> +1.0, bit 0 -> -1.0.  One LOP3 (LUT 0xAE).
+              asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[i]) : "r"(sh), "r"(sign_mask), "r"(kOne));
+            }
+            tmem_st16(tmem_base + lane_addr + col_abuf0 + b * a_cols_per_buf + t * (kBlockK / 2) + jj * 16, r);
+          }
+        }
+      }
+      tc_wait_st();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_afull[b]);
+        mbar_arrive(&bar_empty[s]);
+      }
+
+      if (!seg_last) continue;
+      // ===================================================== epilogue of this (tile, K run)
+      mbar_wait(&bar_dfull, dphase);
+      dphase ^= 1u;
+      tc_fence_after();
+      const int seg_kb0 = kb - (u - seg_u0);  // first K block of this run
+      const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
+      const int64_t n = (int64_t)tile * kTileN + row;
+      // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run of a
+      // CTA can be partial; the runs in between cover whole tiles)
+      const int slot = (seg_u0 == u_begin) ? 0 : 1;
+      float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
+
+      for (int t = 0; t < a.T; ++t) {
+        const float cf = HAS_BASE ? load_coeff(a.coeff, a.coeff_dtype, t) : 1.0f;
+        for (int c8 = 0; c8 < a.mp / 8; ++c8) {
+          if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
+          if (c8 * 8 >= a.m) continue;
+          float dv[8], bv[8];
+          tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            bv[i] = 0.f;
+            if (HAS_BASE && c8 * 8 + i < a.m) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
+          }
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ii = c8 * 8 + i;
+            if (ii >= a.m) continue;
+            const int r = t * a.m + ii;
+            const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
+            if (full_k) {
+              if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+            } else {
+              part[(size_t)r * kTileN + row] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      if (full_k) continue;
+
+      // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+      if (ut == 0) {
+        // contributors = CTAs whose unit range intersects this tile
+        const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
+        // CTA index owning a unit: invert c*U + min(c,R)
+        auto owner = [&](int unit) {
+          const int big = a.units_rem * (a.units_per_cta + 1);
+          return unit < big ? unit / (a.units_per_cta + 1) : a.units_rem + (unit - big) / a.units_per_cta;
+        };
+        const unsigned contributors = (unsigned)(owner(last_unit) - owner(first_unit) + 1);
+        const unsigned old = atomicAdd(&a.counters[tile], 1u);
+        s_is_last = (old == contributors - 1u) ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+      if (!s_is_last) continue;
+      __threadfence();
+      {
+        const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
+        const int big = a.units_rem * (a.units_per_cta + 1);
+        const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
+        const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
+        // thread -> (row, rows split between the two warps of the quadrant)
+        for (int r = grp; r < a.rows; r += 2) {
+          float v = 0.f;
+          for (int c = c_first; c <= c_last; ++c) {
+            const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
+            v += __ldcg(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN + row);
+          }
+          if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+        }
+        if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct DeviceInfo {
+  int sms = 0, smem_optin = 0, cc_major = 0;
+};
+DeviceInfo device_info() {
+  static DeviceInfo info[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DeviceInfo{};
+  std::lock_guard<std::mutex> lock(mu);
+  if (info[dev].sms == 0) {
+    cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&info[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  }
+  return info[dev];
+}
+
+struct UmmaPlan {
+  bool ok = false;
+  const char* why = "";
+  int mp = 0, ntb = 0, stages = 0;
+  uint32_t stage_bytes = 0, off_masks = 0, off_x = 0, off_xp = 0, xp_buf_bytes = 0, smem_bytes = 0, tx_bytes = 0;
+};
+
+UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base) {
+  UmmaPlan p;
+  const int64_t rows = T * m;
+  if (rows > kMaxRows) { p.why = "more than 128 rows per launch"; return p; }
+  if (T > 1 && m > 16) { p.why = "multi-tenant launches support at most 16 rows per tenant"; return p; }
+  if (N % 4 != 0) { p.why = "N must be a multiple of 4 (TMA row pitch of the sign words)"; return p; }
+  if (K % 32 != 0) { p.why = "K must be a multiple of 32"; return p; }
+  if ((N + kTileN - 1) / kTileN > (int64_t)(kWsCounterBytes / sizeof(unsigned))) { p.why = "too many N tiles"; return p; }
+  p.mp = (int)((m + 15) / 16 * 16);
+  p.ntb = (int)((rows + 15) / 16 * 16);
+  const int64_t a_cols = kNumABuf * T * (kBlockK / 2);
+  if (p.ntb + T * p.mp + a_cols > (int64_t)kTmemCols) { p.why = "accumulators + sign operand buffers exceed 512 TMEM columns"; return p; }
+  const uint32_t w_bytes = has_base ? kTileN * kBlockK * 2 : 0;
+  const uint32_t m_bytes = (uint32_t)T * (kBlockK / 32) * kTileN * 4;
+  const uint32_t x_bytes = (uint32_t)p.ntb * 128;
+  auto up1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  p.off_masks = w_bytes;
+  p.off_x = up1k(w_bytes + m_bytes);
+  p.stage_bytes = up1k(p.off_x + x_bytes);
+  p.tx_bytes = w_bytes + m_bytes + x_bytes;
+  p.xp_buf_bytes = (uint32_t)T * p.mp * 128;
+  const uint32_t budget = 216u * 1024u;
+  const uint32_t fixed = kNumABuf * p.xp_buf_bytes;
+  if (fixed + 3 * p.stage_bytes > budget) { p.why = "tile does not fit in shared memory"; return p; }
+  p.stages = (int)((budget - fixed) / p.stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.off_xp = p.stages * p.stage_bytes;
+  p.smem_bytes = p.off_xp + fixed + 1024;  // + slack for the manual 1 KiB alignment
+  p.ok = true;
+  return p;
+}
+
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BD_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return BD_OK;
+}
+
+template <typename T16, bool HAS_BASE>
+int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const CUtensorMap& tw, const CUtensorMap& tm, const CUtensorMap& tx, const UmmaArgs& args,
+                 int grid) {
+  auto kern = fwd_umma_kernel<T16, HAS_BASE>;
+  static std::once_flag once;  // one per template instantiation
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); });
+  if (attr_err != cudaSuccess) return fail(BD_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+  kern<<<grid, kThreads, plan.smem_bytes, p.stream>>>(tw, tm, tx, args);
+  count_launch();
+  return check_launch("fwd_umma_kernel");
+}
+
+}  // namespace
+
+bool umma_supports(const FwdProblem& p, const char** why) {
+  int64_t T = p.T, m = p.m;
+  if (p.mask_tenant_stride == 0 && T > 1) {
+    if (p.w) { *why = "broadcast sign matrix with several tenants"; return false; }
+    m = T * m; T = 1;  // binary_bmm with one shared sign matrix == one tenant with T*m rows
+  }
+  if (p.dtype != BD_BF16 && p.dtype != BD_FP16) { *why = "dtype"; return false; }
+  UmmaPlan plan = plan_umma(T, m, p.K, p.N, p.w != nullptr);
+  if (!plan.ok) { *why = plan.why; return false; }
+  *why = "";
+  return true;
+}
+
+size_t umma_workspace_bytes(int64_t rows, int64_t N) {
+  (void)N;
+  if (rows > kMaxRows) rows = kMaxRows;
+  return kWsScratchOffset + (size_t)160 * 2 * rows * kTileN * sizeof(float);  // up to 160 SMs
+}
+
+int launch_fwd_umma(const FwdProblem& p) {
+  int64_t T = p.T, m = p.m;
+  int64_t tenant_stride = p.mask_tenant_stride;
+  if (tenant_stride == 0 && T > 1) { m = T * m; T = 1; }
+  if (tenant_stride == 0) tenant_stride = (p.K / 32) * p.N;
+  const bool has_base = p.w != nullptr;
+  UmmaPlan plan = plan_umma(T, m, p.K, p.N, has_base);
+  if (!plan.ok) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: %s", plan.why);
+  DeviceInfo di = device_info();
+  if (di.cc_major != 10) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel needs an sm_100 device (found compute capability %d.x)", di.cc_major);
+  if ((uint32_t)di.smem_optin < plan.smem_bytes) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel needs %u bytes of shared memory", plan.smem_bytes);
+  if (di.sms > 160) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: more SMs than the workspace layout assumes");
+
+  const int64_t rows = T * m;
+  UmmaArgs a{};
+  a.coeff = p.coeff; a.coeff_dtype = p.coeff_dtype; a.y = p.y;
+  a.T = (int)T; a.m = (int)m; a.rows = (int)rows; a.mp = plan.mp; a.ntb = plan.ntb;
+  a.K = (int)p.K; a.N = (int)p.N;
+  a.kblocks = (int)((p.K + kBlockK - 1) / kBlockK);
+  a.n_tiles = (int)((p.N + kTileN - 1) / kTileN);
+  a.total_units = a.n_tiles * a.kblocks;
+  const int grid = a.total_units < di.sms ? a.total_units : di.sms;
+  a.units_per_cta = a.total_units / grid;
+  a.units_rem = a.total_units % grid;
+  a.stages = plan.stages; a.stage_bytes = plan.stage_bytes; a.off_masks = plan.off_masks; a.off_x = plan.off_x;
+  a.off_xp = plan.off_xp; a.xp_buf_bytes = plan.xp_buf_bytes; a.tx_bytes = plan.tx_bytes;
+  const size_t need = kWsScratchOffset + (size_t)grid * 2 * rows * kTileN * sizeof(float);
+  if (!p.workspace || p.workspace_bytes < need) return fail(BD_ERR_WORKSPACE, "tcgen05 forward needs %zu workspace bytes, got %zu", need, p.workspace_bytes);
+  a.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p.workspace) + kWsUmmaCounterOffset);
+  a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + kWsScratchOffset);
+
+  const CUtensorMapDataType dt16 = p.dtype == BD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  alignas(64) CUtensorMap tw{}, tm{}, tx{};
+  int rc;
+  if (has_base) {
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N}, str[1] = {(cuuint64_t)p.K * 2};
+    cuuint32_t box[2] = {kBlockK, kTileN};
+    if ((rc = encode_map(&tw, dt16, 2, p.w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)(p.K / 32), (cuuint64_t)T};
+    cuuint64_t str[2] = {(cuuint64_t)p.N * 4, (cuuint64_t)tenant_stride * 4};
+    cuuint32_t box[3] = {kTileN, kBlockK / 32, (cuuint32_t)T};
+    if ((rc = encode_map(&tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, p.masks, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "masks"))) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)rows}, str[1] = {(cuuint64_t)p.K * 2};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)plan.ntb};
+    if ((rc = encode_map(&tx, dt16, 2, p.x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
+  }
+  if (p.dtype == BD_BF16)
+    return has_base ? launch_typed<__nv_bfloat16, true>(p, plan, tw, tm, tx, a, grid) : launch_typed<__nv_bfloat16, false>(p, plan, tw, tm, tx, a, grid);
+  return has_base ? launch_typed<__half, true>(p, plan, tw, tm, tx, a, grid) : launch_typed<__half, false>(p, plan, tw, tm, tx, a, grid);
+}
+
 }  // namespace bd
