@@ -57,6 +57,10 @@ extern "C" BD_API int bd_abi_version(void) { return BD_ABI_VERSION; }
 extern "C" BD_API const char* bd_last_error(void) { return last_error_ref().c_str(); }
 extern "C" BD_API uint64_t bd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// Bring-up instrumentation (not part of the reference-facing surface): device buffer of 64 x 16 int64 clock64 stamps
+// written by CTA 0 of the tcgen05 kernel; nullptr disables it.
+extern "C" BD_API void bd_debug_set_trace(void* device_buffer) { umma_set_trace(reinterpret_cast<long long*>(device_buffer)); }
+
 extern "C" BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n) {
   if (max_rows <= 0 || max_n <= 0) return 0;
   size_t a = simt_workspace_bytes(max_rows, max_n), b = umma_workspace_bytes(max_rows, max_n);
@@ -66,6 +70,7 @@ extern "C" BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n) {
 extern "C" BD_API int bd_select_kernel(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, int has_base) {
   FwdProblem p{};
   p.dtype = dtype; p.T = T; p.m = m; p.K = K; p.N = N;
+  p.mask_tenant_stride = (K / 32) * N;  // contiguous [T, K/32, N] sign words
   p.w = has_base ? reinterpret_cast<const void*>(16) : nullptr;  // only null-ness and alignment are inspected
   p.x = p.y = reinterpret_cast<void*>(16);
   const char* why = "";

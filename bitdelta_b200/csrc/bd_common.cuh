@@ -95,5 +95,6 @@ int launch_fwd_umma(const FwdProblem& p);
 bool umma_supports(const FwdProblem& p, const char** why);
 size_t simt_workspace_bytes(int64_t rows, int64_t N);
 size_t umma_workspace_bytes(int64_t rows, int64_t N);
+void umma_set_trace(long long* buf);
 
 }  // namespace bd

@@ -40,7 +40,7 @@ constexpr int kTileN = 128;   // weight rows per tile (MMA M)
 constexpr int kBlockK = 64;   // K per unit (one 128-byte swizzle atom of bf16)
 constexpr int kNumABuf = 2;   // TMEM A-operand buffers
 constexpr int kUnpackWarps = 8;
-constexpr int kThreads = 32 * (2 + kUnpackWarps);
+constexpr int kThreads = 32 * (3 + kUnpackWarps);  // producer, MMA issuer, 8 unpack/epilogue warps, activation-permute warp
 constexpr int kMaxStages = 8;
 constexpr int kMaxRows = 128;  // rows (tokens) per launch
 constexpr uint32_t kTmemCols = 512;
@@ -185,9 +185,49 @@ struct UmmaArgs {
   uint32_t stage_bytes, off_masks, off_x;     // stage layout: [W tile][masks][X tile]
   uint32_t off_xp, xp_buf_bytes;              // permuted activation tiles, one per A buffer
   uint32_t tx_bytes;
+  long long* trace;  // optional [64 units][16 slots] clock64 timestamps of CTA 0 (bring-up instrumentation)
 };
 
+__device__ __forceinline__ void trace_mark(const UmmaArgs& a, int it, int slot) {
+  if (a.trace != nullptr && blockIdx.x == 0 && it < 64) a.trace[it * 16 + slot] = clock64();
+}
 __device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return c * a.units_per_cta + min(c, a.units_rem); }
+
+// Ring-buffer cursor: index + phase bit, advanced without integer division.
+struct Ring {
+  int idx = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// The 64-bit shared-memory descriptors differ only in their low word (start address >> 4); the high word is constant:
+// SBO = 1024 B (>> 4 = 64) at bits [32,46), version 1 at bit 46, SWIZZLE_128B (2) at bits [61,64).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 template <typename T16, bool HAS_BASE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -203,6 +243,11 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int u_begin = cta_unit_begin(a, cta), u_end = cta_unit_begin(a, cta + 1);
+  const int tile0 = u_begin / a.kblocks, kb0 = u_begin - tile0 * a.kblocks;  // the only division by kblocks
+  // The activation permutation is done by the dedicated warp alone when it is small (decode), otherwise shared with
+  // the unpack warps.
+  const int xjobs = a.rows * 8;
+  const bool xperm_shared = xjobs > 64;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -211,10 +256,10 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     prefetch_tmap(&tmap_x);
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1 + kUnpackWarps);
+      mbar_init(&bar_empty[s], 2 + kUnpackWarps);  // MMA commit + permute warp + unpack warps
     }
     for (int b = 0; b < kNumABuf; ++b) {
-      mbar_init(&bar_afull[b], kUnpackWarps);
+      mbar_init(&bar_afull[b], 1 + kUnpackWarps);  // permute warp + unpack warps
       mbar_init(&bar_aempty[b], 1);
     }
     mbar_init(&bar_dfull, 1);
@@ -234,20 +279,40 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   const uint32_t a_cols_per_buf = (uint32_t)a.T * (kBlockK / 2);
   const uint32_t col_abuf0 = kTmemCols - kNumABuf * a_cols_per_buf;
 
+  // K-permuted copy of the activation rows for A buffer `b` (see the header comment): job = (row r, 16-byte output
+  // chunk c of the 64-K block); out chunk c of a 32-group = x[4c..4c+3] interleaved with x[4c+16..4c+19]; source and
+  // destination tiles use the 128-byte swizzle (chunk index XOR row % 8).
+  auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job) {
+    const int r = job >> 3, c = job & 7;
+    const int g = c >> 2, cc = c & 3;
+    const int ca = 4 * g + (cc >> 1), cb = ca + 2;
+    const uint8_t* src = xsrc + r * 128;
+    const uint2 va = *reinterpret_cast<const uint2*>(src + ((ca ^ (r & 7)) << 4) + ((cc & 1) << 3));
+    const uint2 vb = *reinterpret_cast<const uint2*>(src + ((cb ^ (r & 7)) << 4) + ((cc & 1) << 3));
+    uint4 o;
+    o.x = __byte_perm(va.x, vb.x, 0x5410);
+    o.y = __byte_perm(va.x, vb.x, 0x7632);
+    o.z = __byte_perm(va.y, vb.y, 0x5410);
+    o.w = __byte_perm(va.y, vb.y, 0x7632);
+    const int t = r / a.m, i = r - t * a.m;
+    *reinterpret_cast<uint4*>(xp + (t * a.mp + i) * 128 + ((c ^ (i & 7)) << 4)) = o;
+  };
+
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int it = 0;
-      for (int u = u_begin; u < u_end; ++u, ++it) {
-        const int s = it % a.stages;
-        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
-        const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
-        mbar_wait(&bar_empty[s], ph ^ 1u);
-        uint8_t* st = smem + (size_t)s * a.stage_bytes;
-        mbar_arrive_expect_tx(&bar_full[s], a.tx_bytes);
-        if (HAS_BASE) tma_load_2d(st, &tmap_w, &bar_full[s], kb * kBlockK, tile * kTileN, kEvictFirst);
-        tma_load_3d(st + a.off_masks, &tmap_m, &bar_full[s], tile * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
-        tma_load_2d(st + a.off_x, &tmap_x, &bar_full[s], kb * kBlockK, 0, kEvictLast);
+      Ring st;
+      int tile = tile0, kb = kb0;
+      for (int u = u_begin; u < u_end; ++u) {
+        mbar_wait(&bar_empty[st.idx], st.phase ^ 1u);
+        trace_mark(a, u - u_begin, 8);
+        uint8_t* sp = smem + (size_t)st.idx * a.stage_bytes;
+        mbar_arrive_expect_tx(&bar_full[st.idx], a.tx_bytes);
+        if (HAS_BASE) tma_load_2d(sp, &tmap_w, &bar_full[st.idx], kb * kBlockK, tile * kTileN, kEvictFirst);
+        tma_load_3d(sp + a.off_masks, &tmap_m, &bar_full[st.idx], tile * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
+        tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], kb * kBlockK, 0, kEvictLast);
+        st.advance(a.stages);
+        if (++kb == a.kblocks) { kb = 0; ++tile; }
       }
     }
   } else if (warp == 1) {
@@ -255,40 +320,67 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     constexpr int fmt = std::is_same<T16, __nv_bfloat16>::value ? 1 : 0;
     const uint32_t idesc_base = make_idesc(fmt, a.ntb);
     const uint32_t idesc_delta = make_idesc(fmt, a.mp);
-    int it = 0;
-    uint32_t dphase = 0;
-    (void)dphase;
-    for (int u = u_begin; u < u_end; ++u, ++it) {
-      const int s = it % a.stages, b = it % kNumABuf;
-      const uint32_t ph = (uint32_t)(it / a.stages) & 1u, aph = (uint32_t)(it / kNumABuf) & 1u;
-      const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
+    const bool leader = elect_one();
+    // descriptor low words (address >> 4) of stage 0 / A buffer 0 and their strides
+    const uint32_t w_lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4, stage_lo = a.stage_bytes >> 4;
+    const uint32_t x_off_lo = a.off_x >> 4;
+    const uint32_t xp_lo0 = (smem_u32(smem + a.off_xp) & 0x3FFFFu) >> 4, xp_buf_lo = a.xp_buf_bytes >> 4, xp_t_lo = (uint32_t)a.mp * 8;
+    Ring st, ab;
+    int kb = kb0;
+    for (int u = u_begin; u < u_end; ++u) {
       const bool seg_first = (u == u_begin) || (kb == 0);
       const bool seg_last = (u + 1 == u_end) || (kb + 1 == a.kblocks);
-      mbar_wait(&bar_full[s], ph);
-      mbar_wait(&bar_afull[b], aph);
+      mbar_wait(&bar_full[st.idx], st.phase);
+      if (lane == 0) trace_mark(a, u - u_begin, 5);
+      mbar_wait(&bar_afull[ab.idx], ab.phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = smem_u32(smem + (size_t)s * a.stage_bytes);
-        const uint32_t xp = smem_u32(smem + a.off_xp + (size_t)b * a.xp_buf_bytes);
+      if (leader) {
+        trace_mark(a, u - u_begin, 6);
+        const uint32_t w_lo = w_lo0 + st.idx * stage_lo;
+        const uint32_t x_lo = w_lo + x_off_lo;
+        const uint32_t xp_lo = xp_lo0 + ab.idx * xp_buf_lo;
+        const uint32_t a_tmem0 = tmem_base + col_abuf0 + ab.idx * a_cols_per_buf;
+        const uint32_t d_base = tmem_base + col_dbase, d_delta = tmem_base + col_ddelta;
+        // k-step outermost: consecutive MMAs go to different accumulators (base, tenant 0, tenant 1, ...)
 #pragma unroll
         for (int ks = 0; ks < kBlockK / 16; ++ks) {
           const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
-          if (HAS_BASE)
-            mma_ss(tmem_base + col_dbase, smem_desc_sw128(st + ks * 32), smem_desc_sw128(st + a.off_x + ks * 32), idesc_base, acc);
-        }
-        for (int t = 0; t < a.T; ++t) {
-#pragma unroll
-          for (int ks = 0; ks < kBlockK / 16; ++ks) {
-            const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
-            mma_ts(tmem_base + col_ddelta + t * a.mp, tmem_base + col_abuf0 + b * a_cols_per_buf + t * (kBlockK / 2) + ks * 8,
-                   smem_desc_sw128(xp + t * a.mp * 128 + ks * 32), idesc_delta, acc);
+          if (HAS_BASE) mma_ss_lo(d_base, w_lo + ks * 2, x_lo + ks * 2, idesc_base, acc);
+          uint32_t d = d_delta, at = a_tmem0 + ks * 8, bl = xp_lo + ks * 2;
+          for (int t = 0; t < a.T; ++t) {
+            mma_ts_lo(d, at, bl, idesc_delta, acc);
+            d += a.mp; at += kBlockK / 2; bl += xp_t_lo;
           }
         }
-        tc_commit(&bar_empty[s]);   // stage (W tile, X tile) may be overwritten once these MMAs retire
-        tc_commit(&bar_aempty[b]);  // so may the TMEM A buffer and its permuted-X tiles
+        tc_commit(&bar_empty[st.idx]);   // stage (W tile, X tile) may be overwritten once these MMAs retire
+        tc_commit(&bar_aempty[ab.idx]);  // so may the TMEM A buffer and its permuted-X tiles
         if (seg_last) tc_commit(&bar_dfull);
+        trace_mark(a, u - u_begin, 7);
       }
       __syncwarp();
+      st.advance(a.stages);
+      ab.advance(kNumABuf);
+      if (++kb == a.kblocks) kb = 0;
+    }
+  } else if (warp == 2 + kUnpackWarps) {
+    // ===================================================== activation-permute warp
+    Ring st, ab;
+    for (int u = u_begin; u < u_end; ++u) {
+      mbar_wait(&bar_full[st.idx], st.phase);
+      mbar_wait(&bar_aempty[ab.idx], ab.phase ^ 1u);
+      if (!xperm_shared) {
+        const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
+        uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
+        for (int job = lane; job < xjobs; job += 32) xperm_job(xsrc, xp, job);
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_afull[ab.idx]);
+        mbar_arrive(&bar_empty[st.idx]);
+      }
+      st.advance(a.stages);
+      ab.advance(kNumABuf);
     }
   } else {
     // ===================================================== unpack + epilogue warps
@@ -302,48 +394,35 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     T16* __restrict__ y = reinterpret_cast<T16*>(a.y);
     uint32_t sign_mask = 0x80008000u;
     asm volatile("" : "+r"(sign_mask));  // keep the mask in a register so mask + constant fit one LOP3
-    int it = 0, seg_u0 = u_begin;
+    Ring st, ab;
+    int tile = tile0, kb = kb0, seg_kb0 = kb0;
+    bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
     uint32_t dphase = 0;
-    for (int u = u_begin; u < u_end; ++u, ++it) {
-      const int s = it % a.stages, b = it % kNumABuf;
-      const uint32_t ph = (uint32_t)(it / a.stages) & 1u, aph = (uint32_t)(it / kNumABuf) & 1u;
-      const int tile = u / a.kblocks, kb = u - tile * a.kblocks;
-      if (kb == 0) seg_u0 = u;  // a new (tile, K run) starts here (or at u_begin)
+    for (int u = u_begin; u < u_end; ++u) {
+      const int it = u - u_begin;
       const bool seg_last = (u + 1 == u_end) || (kb + 1 == a.kblocks);
-      mbar_wait(&bar_full[s], ph);
-      mbar_wait(&bar_aempty[b], aph ^ 1u);
+      const bool tr = (uw == 0 && lane == 0);
+      mbar_wait(&bar_full[st.idx], st.phase);
+      if (tr) trace_mark(a, it, 0);
+      mbar_wait(&bar_aempty[ab.idx], ab.phase ^ 1u);
       tc_fence_after();
-      const uint8_t* st = smem + (size_t)s * a.stage_bytes;
+      if (tr) trace_mark(a, it, 1);
+      const uint8_t* sp = smem + (size_t)st.idx * a.stage_bytes;
 
-      // (1) K-permuted copy of every tenant's activation rows: out chunk c of a 32-group = x[4c..4c+3] interleaved with
-      //     x[4c+16..4c+19]; both tiles use the 128-byte swizzle (16-byte chunk index XOR row % 8).
-      {
-        uint8_t* xp = smem + a.off_xp + (size_t)b * a.xp_buf_bytes;
-        const int jobs = a.rows * 8;
-        for (int job = ut; job < jobs; job += kUnpackWarps * 32) {
-          const int r = job >> 3, c = job & 7;          // r = global row, c = output chunk (0..7) of the 64-K block
-          const int g = c >> 2, cc = c & 3;             // 32-group, chunk inside the group
-          const int ca = 4 * g + (cc >> 1), cb = ca + 2;  // source chunks holding x[4cc..] and x[4cc+16..]
-          const uint8_t* src = st + a.off_x + r * 128;
-          const uint2 va = *reinterpret_cast<const uint2*>(src + ((ca ^ (r & 7)) << 4) + ((cc & 1) << 3));
-          const uint2 vb = *reinterpret_cast<const uint2*>(src + ((cb ^ (r & 7)) << 4) + ((cc & 1) << 3));
-          uint4 o;
-          o.x = __byte_perm(va.x, vb.x, 0x5410);  // (a0, b0)
-          o.y = __byte_perm(va.x, vb.x, 0x7632);  // (a1, b1)
-          o.z = __byte_perm(va.y, vb.y, 0x5410);  // (a2, b2)
-          o.w = __byte_perm(va.y, vb.y, 0x7632);  // (a3, b3)
-          const int t = r / a.m, i = r - t * a.m;
-          *reinterpret_cast<uint4*>(xp + (t * a.mp + i) * 128 + ((c ^ (i & 7)) << 4)) = o;
-        }
+      if (xperm_shared) {  // (1) large row counts: the unpack warps share the activation permutation
+        uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
+        for (int job = ut; job < xjobs; job += kUnpackWarps * 32) xperm_job(sp + a.off_x, xp, job);
       }
+      if (tr) trace_mark(a, it, 2);
 
       // (2) sign words -> +-1.0 pairs -> TMEM A operand
       {
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(st + a.off_masks);
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(sp + a.off_masks) + row;
+        const uint32_t ta = tmem_base + lane_addr + col_abuf0 + ab.idx * a_cols_per_buf;
         for (int t = grp; t < a.T; t += 2) {
 #pragma unroll
           for (int jj = 0; jj < kBlockK / 32; ++jj) {
-            const uint32_t w = mw[(t * (kBlockK / 32) + jj) * kTileN + row];
+            const uint32_t w = mw[(t * (kBlockK / 32) + jj) * kTileN];
             uint32_t r[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -351,96 +430,94 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               // r = (~sh & 0x80008000) | one : sign = ~bit, bit 1 -> +1.0, bit 0 -> -1.0.  One LOP3 (LUT 0xAE).
               asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[i]) : "r"(sh), "r"(sign_mask), "r"(kOne));
             }
-            tmem_st16(tmem_base + lane_addr + col_abuf0 + b * a_cols_per_buf + t * (kBlockK / 2) + jj * 16, r);
+            tmem_st16(ta + t * (kBlockK / 2) + jj * 16, r);
           }
         }
       }
+      if (tr) trace_mark(a, it, 3);
       tc_wait_st();
-      fence_proxy_async();
+      if (xperm_shared) fence_proxy_async();
       tc_fence_before();
       __syncwarp();
+      if (tr) trace_mark(a, it, 4);
       if (lane == 0) {
-        mbar_arrive(&bar_afull[b]);
-        mbar_arrive(&bar_empty[s]);
+        mbar_arrive(&bar_afull[ab.idx]);
+        mbar_arrive(&bar_empty[st.idx]);
       }
+      st.advance(a.stages);
+      ab.advance(kNumABuf);
 
-      if (!seg_last) continue;
-      // ===================================================== epilogue of this (tile, K run)
-      mbar_wait(&bar_dfull, dphase);
-      dphase ^= 1u;
-      tc_fence_after();
-      const int seg_kb0 = kb - (u - seg_u0);  // first K block of this run
-      const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
-      const int64_t n = (int64_t)tile * kTileN + row;
-      // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run of a
-      // CTA can be partial; the runs in between cover whole tiles)
-      const int slot = (seg_u0 == u_begin) ? 0 : 1;
-      float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
+      if (seg_last) {
+        // ===================================================== epilogue of this (tile, K run)
+        mbar_wait(&bar_dfull, dphase);
+        dphase ^= 1u;
+        tc_fence_after();
+        const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
+        const int64_t n = (int64_t)tile * kTileN + row;
+        // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run
+        // of a CTA can be partial; the runs in between cover whole tiles)
+        const int slot = seg_is_first ? 0 : 1;
+        float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
 
-      for (int t = 0; t < a.T; ++t) {
-        const float cf = HAS_BASE ? load_coeff(a.coeff, a.coeff_dtype, t) : 1.0f;
-        for (int c8 = 0; c8 < a.mp / 8; ++c8) {
-          if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
-          if (c8 * 8 >= a.m) continue;
-          float dv[8], bv[8];
-          tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
+        for (int t = 0; t < a.T; ++t) {
+          const float cf = HAS_BASE ? load_coeff(a.coeff, a.coeff_dtype, t) : 1.0f;
+          for (int c8 = 0; c8 < a.mp / 8; ++c8) {
+            if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
+            if (c8 * 8 >= a.m) continue;
+            float dv[8], bv[8];
+            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            bv[i] = 0.f;
-            if (HAS_BASE && c8 * 8 + i < a.m) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
-          }
-          tc_wait_ld();
+            for (int i = 0; i < 8; ++i) {
+              bv[i] = 0.f;
+              if (HAS_BASE && c8 * 8 + i < a.m) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
+            }
+            tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ii = c8 * 8 + i;
-            if (ii >= a.m) continue;
-            const int r = t * a.m + ii;
-            const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
-            if (full_k) {
-              if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
-            } else {
-              part[(size_t)r * kTileN + row] = v;
+            for (int i = 0; i < 8; ++i) {
+              const int ii = c8 * 8 + i;
+              if (ii >= a.m) continue;
+              const int r = t * a.m + ii;
+              const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
+              if (full_k) {
+                if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+              } else {
+                part[(size_t)r * kTileN + row] = v;
+              }
             }
           }
         }
-      }
-      tc_fence_before();
-      if (full_k) continue;
+        tc_fence_before();
 
-      // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-      if (ut == 0) {
-        // contributors = CTAs whose unit range intersects this tile
-        const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
-        // CTA index owning a unit: invert c*U + min(c,R)
-        auto owner = [&](int unit) {
-          const int big = a.units_rem * (a.units_per_cta + 1);
-          return unit < big ? unit / (a.units_per_cta + 1) : a.units_rem + (unit - big) / a.units_per_cta;
-        };
-        const unsigned contributors = (unsigned)(owner(last_unit) - owner(first_unit) + 1);
-        const unsigned old = atomicAdd(&a.counters[tile], 1u);
-        s_is_last = (old == contributors - 1u) ? 1u : 0u;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-      if (!s_is_last) continue;
-      __threadfence();
-      {
-        const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
-        const int big = a.units_rem * (a.units_per_cta + 1);
-        const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
-        const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
-        // thread -> (row, rows split between the two warps of the quadrant)
-        for (int r = grp; r < a.rows; r += 2) {
-          float v = 0.f;
-          for (int c = c_first; c <= c_last; ++c) {
-            const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
-            v += __ldcg(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN + row);
+        if (!full_k) {
+          // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
+          const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
+          const int big = a.units_rem * (a.units_per_cta + 1);  // units owned by the CTAs that got one extra unit
+          const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
+          const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+          if (ut == 0) {
+            const unsigned old = atomicAdd(&a.counters[tile], 1u);
+            s_is_last = (old == (unsigned)(c_last - c_first)) ? 1u : 0u;
           }
-          if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+          if (s_is_last) {
+            __threadfence();
+            for (int r = grp; r < a.rows; r += 2) {  // thread -> weight row; the two warps of a quadrant split the rows
+              float v = 0.f;
+              for (int c = c_first; c <= c_last; ++c) {
+                const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
+                v += __ldcg(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN + row);
+              }
+              if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+            }
+            if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
+          }
         }
-        if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
+        seg_is_first = false;
       }
+      if (++kb == a.kblocks) { kb = 0; ++tile; }
+      if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
     }
   }
 
@@ -469,6 +546,8 @@ EncodeTiledFn get_encode_fn() {
   });
   return fn;
 }
+
+long long* g_trace_buf = nullptr;
 
 struct DeviceInfo {
   int sms = 0, smem_optin = 0, cc_major = 0;
@@ -552,6 +631,13 @@ int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const CUtensorMap& t
 
 }  // namespace
 
+// Largest number of tenants (<= T) that one launch can take at m rows per tenant; 0 if even one does not fit.
+static int tenants_per_launch(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base) {
+  for (int64_t g = T < 8 ? T : 8; g >= 1; --g)
+    if (plan_umma(g, m, K, N, has_base).ok) return (int)g;
+  return 0;
+}
+
 bool umma_supports(const FwdProblem& p, const char** why) {
   int64_t T = p.T, m = p.m;
   if (p.mask_tenant_stride == 0 && T > 1) {
@@ -559,7 +645,9 @@ bool umma_supports(const FwdProblem& p, const char** why) {
     m = T * m; T = 1;  // binary_bmm with one shared sign matrix == one tenant with T*m rows
   }
   if (p.dtype != BD_BF16 && p.dtype != BD_FP16) { *why = "dtype"; return false; }
-  UmmaPlan plan = plan_umma(T, m, p.K, p.N, p.w != nullptr);
+  // Problems larger than one launch are decomposed by launch_fwd_umma (tenant groups, then 128-row chunks), so only
+  // the per-launch constraints matter here: check the smallest piece.
+  UmmaPlan plan = plan_umma(1, m < kMaxRows ? m : kMaxRows, p.K, p.N, p.w != nullptr);
   if (!plan.ok) { *why = plan.why; return false; }
   *why = "";
   return true;
@@ -571,10 +659,9 @@ size_t umma_workspace_bytes(int64_t rows, int64_t N) {
   return kWsScratchOffset + (size_t)160 * 2 * rows * kTileN * sizeof(float);  // up to 160 SMs
 }
 
-int launch_fwd_umma(const FwdProblem& p) {
+static int launch_one(const FwdProblem& p) {
   int64_t T = p.T, m = p.m;
   int64_t tenant_stride = p.mask_tenant_stride;
-  if (tenant_stride == 0 && T > 1) { m = T * m; T = 1; }
   if (tenant_stride == 0) tenant_stride = (p.K / 32) * p.N;
   const bool has_base = p.w != nullptr;
   UmmaPlan plan = plan_umma(T, m, p.K, p.N, has_base);
@@ -601,6 +688,7 @@ int launch_fwd_umma(const FwdProblem& p) {
   if (!p.workspace || p.workspace_bytes < need) return fail(BD_ERR_WORKSPACE, "tcgen05 forward needs %zu workspace bytes, got %zu", need, p.workspace_bytes);
   a.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p.workspace) + kWsUmmaCounterOffset);
   a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + kWsScratchOffset);
+  a.trace = g_trace_buf;
 
   const CUtensorMapDataType dt16 = p.dtype == BD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   alignas(64) CUtensorMap tw{}, tm{}, tx{};
@@ -624,6 +712,46 @@ int launch_fwd_umma(const FwdProblem& p) {
   if (p.dtype == BD_BF16)
     return has_base ? launch_typed<__nv_bfloat16, true>(p, plan, tw, tm, tx, a, grid) : launch_typed<__nv_bfloat16, false>(p, plan, tw, tm, tx, a, grid);
   return has_base ? launch_typed<__half, true>(p, plan, tw, tm, tx, a, grid) : launch_typed<__half, false>(p, plan, tw, tm, tx, a, grid);
+}
+
+void umma_set_trace(long long* buf) { g_trace_buf = buf; }
+
+// Decomposes a problem into launches the kernel takes: tenant groups that fit the TMEM budget, then 128-row chunks of a
+// single tenant.  Sub-launches are stream-ordered and share the workspace (each leaves its counters at zero).
+int launch_fwd_umma(const FwdProblem& p0) {
+  FwdProblem p = p0;
+  if (p.mask_tenant_stride == 0 && p.T > 1) { p.m = p.T * p.m; p.T = 1; }
+  const size_t esz = 2;  // bf16 / fp16
+  const size_t csz = p.coeff_dtype == BD_FP32 ? 4 : 2;
+  const bool has_base = p.w != nullptr;
+  if (plan_umma(p.T, p.m, p.K, p.N, has_base).ok) return launch_one(p);
+  if (p.T > 1) {
+    int g = p.m <= 16 ? tenants_per_launch(p.T, p.m, p.K, p.N, has_base) : 1;
+    if (g < 1) g = 1;
+    for (int64_t t0 = 0; t0 < p.T; t0 += g) {
+      FwdProblem s = p;
+      s.T = (p.T - t0 < g) ? p.T - t0 : g;
+      s.x = reinterpret_cast<const char*>(p.x) + (size_t)t0 * p.m * p.K * esz;
+      s.y = reinterpret_cast<char*>(p.y) + (size_t)t0 * p.m * p.N * esz;
+      s.masks = p.masks + t0 * p.mask_tenant_stride;
+      if (p.coeff) s.coeff = reinterpret_cast<const char*>(p.coeff) + (size_t)t0 * csz;
+      int rc = launch_fwd_umma(s);
+      if (rc) return rc;
+    }
+    return BD_OK;
+  }
+  if (p.m > kMaxRows) {
+    for (int64_t r0 = 0; r0 < p.m; r0 += kMaxRows) {
+      FwdProblem s = p;
+      s.m = (p.m - r0 < kMaxRows) ? p.m - r0 : kMaxRows;
+      s.x = reinterpret_cast<const char*>(p.x) + (size_t)r0 * p.K * esz;
+      s.y = reinterpret_cast<char*>(p.y) + (size_t)r0 * p.N * esz;
+      int rc = launch_one(s);
+      if (rc) return rc;
+    }
+    return BD_OK;
+  }
+  return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: %s", plan_umma(p.T, p.m, p.K, p.N, has_base).why);
 }
 
 }  // namespace bd

@@ -110,6 +110,10 @@ BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n);
 /* Which kernel BD_KERNEL_AUTO would pick for this problem (BD_KERNEL_SIMT or BD_KERNEL_UMMA). */
 BD_API int bd_select_kernel(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, int has_base);
 
+/* Bring-up instrumentation: device buffer of 64 x 16 int64 clock64 stamps written by CTA 0 of the tcgen05 kernel
+ * (per work unit: barrier waits, unpack, MMA issue); NULL disables it.  Not used by the Python surface. */
+BD_API void bd_debug_set_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,48 +53,58 @@ void oracle_fwd_batched_bf16(const uint16_t* x, const uint16_t* w, const int32_t
                              int64_t T, int64_t m, int64_t K, int64_t N, int threads) {
   const int64_t rows = T * m;
   float* xf = (float*)malloc(sizeof(float) * rows * K);
+  float* yd = (float*)malloc(sizeof(float) * rows * N); /* delta product, combined with the base product at the end */
   for (int64_t i = 0; i < rows * K; ++i) xf[i] = bf16_to_f32(x[i]);
-  const int64_t NB = 64; /* columns per work item: one 256-byte run of sign words per (tenant, j) */
+  const int64_t NB = 32; /* columns per work item: one 128-byte run of sign words per (tenant, j) */
   const int64_t nblocks = (N + NB - 1) / NB;
 #ifdef _OPENMP
   omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
+  /* work items: (column block) x (part), part 0 = base product for every row, part t+1 = tenant t's delta product */
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
   for (int64_t nb = 0; nb < nblocks; ++nb) {
-    const int64_t n0 = nb * NB, n1 = (n0 + NB < N) ? n0 + NB : N;
-    /* base product: x . w^T (w may be NULL for the delta-only binary_bmm) */
-    for (int64_t r = 0; r < rows; ++r)
-      for (int64_t n = n0; n < n1; ++n) {
-        float acc = 0.f;
-        if (w) {
-          const uint16_t* wr = w + n * K;
-          const float* xr = xf + r * K;
-          for (int64_t k = 0; k < K; ++k) acc += xr[k] * bf16_to_f32(wr[k]);
-        }
-        y[r * N + n] = acc;
-      }
-    /* delta product: x . (2*bits-1), tenant by tenant */
-    for (int64_t t = 0; t < T; ++t) {
-      const int32_t* mt = masks + t * (K / 32) * N;
-      for (int64_t i = 0; i < m; ++i) {
-        const float* xr = xf + (t * m + i) * K;
-        float acc[64];
-        for (int64_t c = 0; c < NB; ++c) acc[c] = 0.f;
-        for (int64_t j = 0; j < K / 32; ++j) {
-          const int32_t* wj = mt + j * N + n0;
-          const float* xj = xr + j * 32;
-          for (int b = 0; b < 32; ++b) {
-            const float xv = xj[b];
-            for (int64_t c = 0; c < n1 - n0; ++c) acc[c] += ((wj[c] >> b) & 1) ? xv : -xv;
+    for (int64_t part = 0; part <= T; ++part) {
+      const int64_t n0 = nb * NB, n1 = (n0 + NB < N) ? n0 + NB : N;
+      if (part == 0) {
+        /* base product: x . w^T (w may be NULL for the delta-only binary_bmm) */
+        for (int64_t r = 0; r < rows; ++r)
+          for (int64_t n = n0; n < n1; ++n) {
+            float acc = 0.f;
+            if (w) {
+              const uint16_t* wr = w + n * K;
+              const float* xr = xf + r * K;
+              for (int64_t k = 0; k < K; ++k) acc += xr[k] * bf16_to_f32(wr[k]);
+            }
+            y[r * N + n] = acc;
           }
-        }
-        const float cf = coeff ? coeff[t] : 1.0f;
-        for (int64_t c = 0; c < n1 - n0; ++c) {
-          float* out = &y[(t * m + i) * N + n0 + c];
-          *out = w ? *out + cf * acc[c] : acc[c];
+      } else {
+        /* delta product: x . (2*bits-1) for tenant t */
+        const int64_t t = part - 1;
+        const int32_t* mt = masks + t * (K / 32) * N;
+        for (int64_t i = 0; i < m; ++i) {
+          const float* xr = xf + (t * m + i) * K;
+          float acc[32];
+          for (int64_t c = 0; c < NB; ++c) acc[c] = 0.f;
+          for (int64_t j = 0; j < K / 32; ++j) {
+            const int32_t* wj = mt + j * N + n0;
+            const float* xj = xr + j * 32;
+            for (int b = 0; b < 32; ++b) {
+              const float xv = xj[b];
+              for (int64_t c = 0; c < n1 - n0; ++c) acc[c] += ((wj[c] >> b) & 1) ? xv : -xv;
+            }
+          }
+          for (int64_t c = 0; c < n1 - n0; ++c) yd[(t * m + i) * N + n0 + c] = acc[c];
         }
       }
     }
   }
+  for (int64_t t = 0; t < T; ++t) {
+    const float cf = coeff ? coeff[t] : 1.0f;
+    for (int64_t i = 0; i < m * N; ++i) {
+      const int64_t o = t * m * N + i;
+      y[o] = w ? y[o] + cf * yd[o] : yd[o];
+    }
+  }
+  free(yd);
   free(xf);
 }

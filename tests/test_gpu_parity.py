@@ -205,7 +205,7 @@ def test_binarydiff_forward_reference_vectors(golden, kernel):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("M", [1, 16, 128])
+@pytest.mark.parametrize("M", [1, 16, 128, 300])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_config1_single_4096_linear(kernel, M, dtype):
     # BASELINE config 1 / SURVEY 8d: seed 0, W_base = randn*0.02, W_fine = W_base + randn*0.002, x = randn(1, M, 4096)
@@ -228,7 +228,7 @@ def test_config1_single_4096_linear(kernel, M, dtype):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("N,K,rows", [(50, 32, 3), (64, 64, 1), (200, 96, 9), (1024, 4096, 6), (72, 2080, 17)])
+@pytest.mark.parametrize("N,K,rows", [(50, 32, 3), (64, 64, 1), (200, 96, 9), (1024, 4096, 6), (72, 2080, 17), (132, 160, 128), (4100, 4128, 2)])
 def test_forward_ragged_shapes(kernel, N, K, rows):
     torch.manual_seed(N + K + rows)
     base = (torch.randn(N, K) * 0.05).bfloat16()
@@ -241,16 +241,40 @@ def test_forward_ragged_shapes(kernel, N, K, rows):
     assert_close_to_exact(y, exact, f"ragged {N}x{K}x{rows}")
 
 
-def test_forward_is_deterministic_and_workspace_is_left_clean():
+@pytest.mark.parametrize("kernel", ["simt", "umma"])
+def test_forward_is_deterministic_and_workspace_is_left_clean(kernel):
+    # split-K partials are combined in a fixed order, so repeated launches are bit-identical; the tile counters in the
+    # workspace are reset by the last CTA, so back-to-back launches of different shapes on one workspace stay correct
     torch.manual_seed(1)
     base = (torch.randn(1024, 4096, device=DEV) * 0.02).bfloat16()
     fine = (base.float() + torch.randn_like(base.float()) * 0.002).bfloat16()
     m = bd.BinaryDiff(base, fine)
-    m.kernel = "simt"
+    m.kernel = kernel
+    base2 = (torch.randn(4096, 1024, device=DEV) * 0.02).bfloat16()
+    m2 = bd.BinaryDiff(base2, (base2.float() + torch.randn_like(base2.float()) * 0.002).bfloat16())
+    m2.kernel = kernel
     x = torch.randn(1, 6, 4096, device=DEV).bfloat16()
-    y0 = m(x)
+    x2 = torch.randn(1, 3, 1024, device=DEV).bfloat16()
+    y0, z0 = m(x), m2(x2)
     for _ in range(5):
         assert torch.equal(m(x), y0)
+        assert torch.equal(m2(x2), z0)
+
+
+def test_auto_selects_the_tcgen05_kernel_for_baseline_shapes():
+    from bitdelta_b200 import _lib
+
+    sel = _lib.lib.bd_select_kernel
+    for T, m, K, N in [(6, 1, 4096, 4096), (6, 1, 4096, 1024), (6, 1, 4096, 14336), (6, 1, 14336, 4096),  # Mistral-7B + 6 deltas
+                       (1, 1, 4096, 11008), (1, 1, 11008, 4096), (1, 64, 4096, 4096),                     # Llama-2-7B + 1 delta
+                       (4, 1, 5120, 13824), (4, 16, 5120, 5120), (1, 128, 8192, 1024)]:
+        assert sel(0, T, m, K, N, 1) == _lib.KERNEL_UMMA, (T, m, K, N)
+        assert sel(1, T, m, K, N, 0) == _lib.KERNEL_UMMA, (T, m, K, N)
+    assert sel(0, 1, 1, 32, 50, 1) == _lib.KERNEL_SIMT       # N % 4 != 0
+    # more rows / tenants than one launch takes are decomposed into several tcgen05 launches
+    assert sel(0, 1, 4096, 4096, 4096, 1) == _lib.KERNEL_UMMA and sel(0, 8, 1, 8192, 8192, 1) == _lib.KERNEL_UMMA
+    with pytest.raises(RuntimeError, match="does not support"):
+        bd.binary_bmm(torch.zeros(1, 1, 32, device=DEV, dtype=torch.bfloat16), torch.zeros(1, 1, 50, device=DEV, dtype=torch.int32), kernel="umma")
 
 
 # ------------------------------------------------------------------------------------------------ multi-tenant modules
@@ -285,10 +309,10 @@ def test_dataparallel_reference_vectors(golden):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("N,K,m", [(1024, 4096, 1), (4096, 14336, 1), (4096, 4096, 3)])
-def test_mistral_shapes_six_tenants(kernel, N, K, m):
-    # BASELINE config 3 shapes (k_proj, down_proj, q_proj), T = 6 tenants, decode rows
-    T = 6
+@pytest.mark.parametrize("N,K,m,T", [(1024, 4096, 1, 6), (4096, 14336, 1, 6), (4096, 4096, 3, 6), (1024, 8192, 1, 8), (512, 1024, 20, 3)])
+def test_mistral_shapes_six_tenants(kernel, N, K, m, T):
+    # BASELINE config 3 shapes (k_proj, down_proj, q_proj), T = 6 tenants, decode rows; config 5's 8 tenants (two
+    # launches of the tcgen05 kernel) and a multi-tenant case with more than 16 rows per tenant (one launch per tenant)
     gen = torch.Generator(device=DEV).manual_seed(N + K + m)
     w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
     masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Prints the per-unit timeline (clock64 deltas) of CTA 0 of the tcgen05 kernel for one launch.  usage: umma_trace.py T m K N"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bitdelta_b200 as bd
+from bitdelta_b200 import _lib
+from bitdelta_b200.diff import _fused_forward
+T, m, K, N = [int(v) for v in sys.argv[1:5]] if len(sys.argv) >= 5 else (6, 1, 4096, 14336)
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+w = (torch.randn(N, K, generator=g, device=dev) * 0.02).bfloat16()
+ms = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=g, device=dev, dtype=torch.int64).to(torch.int32)
+coeff = torch.full((T,), 0.002, device=dev)
+x = torch.randn(T, m, K, generator=g, device=dev).bfloat16()
+for _ in range(3):
+    _fused_forward(x, w, ms, coeff, T, "umma")
+buf = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+_lib.lib.bd_debug_set_trace(buf.data_ptr())
+_fused_forward(x, w, ms, coeff, T, "umma")
+torch.cuda.synchronize()
+_lib.lib.bd_debug_set_trace(None)
+t = buf.cpu().view(64, 16)
+t0 = t[0, 8].item()
+names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty"]
+print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
+print("unit " + " ".join(n.rjust(9) for n in names) + "   | unpack  mma_issue  afull->aempty(+2)")
+for it in range(64):
+    if t[it, 0].item() == 0:
+        break
+    row = [t[it, s].item() - t0 for s in range(9)]
+    extra = ""
+    if it + 2 < 64 and t[it + 2, 1].item():
+        extra = f"{row[4]-row[1]:8d} {row[7]-row[6]:9d} {t[it+2,1].item()-t0-row[6]:9d}"
+    print(f"{it:4d} " + " ".join(str(v).rjust(9) for v in row) + "   | " + extra)
