@@ -24,7 +24,7 @@ EXPORTS = [
     "bd_pack", "bd_unpack", "bd_pack_host", "bd_unpack_host",
     "bd_compress", "bd_fold",
     "bd_binary_bmm", "bd_binarydiff_fwd_batched",
-    "bd_workspace_bytes", "bd_select_kernel", "bd_debug_set_trace",
+    "bd_workspace_bytes", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags",
 ]
 
 
@@ -57,9 +57,11 @@ def _load() -> ctypes.CDLL:
     lib.bd_select_kernel.argtypes = [i32, i64, i64, i64, i64, i32]
     lib.bd_debug_set_trace.argtypes = [vp]
     lib.bd_debug_set_trace.restype = None
+    lib.bd_debug_set_flags.argtypes = [i32, i32]
+    lib.bd_debug_set_flags.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if fn.restype is c.c_int and name not in ("bd_abi_version", "bd_select_kernel", "bd_debug_set_trace"):
+        if fn.restype is c.c_int and name not in ("bd_abi_version", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags"):
             fn.restype = i32
     return lib
 

@@ -61,6 +61,8 @@ extern "C" BD_API uint64_t bd_launch_count(void) { return g_launches.load(std::m
 // written by CTA 0 of the tcgen05 kernel; nullptr disables it.
 extern "C" BD_API void bd_debug_set_trace(void* device_buffer) { umma_set_trace(reinterpret_cast<long long*>(device_buffer)); }
 
+extern "C" BD_API void bd_debug_set_flags(int flags, int load_group) { umma_set_debug(flags, load_group); }
+
 extern "C" BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n) {
   if (max_rows <= 0 || max_n <= 0) return 0;
   size_t a = simt_workspace_bytes(max_rows, max_n), b = umma_workspace_bytes(max_rows, max_n);

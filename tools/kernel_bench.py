@@ -10,6 +10,8 @@ from bitdelta_b200.diff import _fused_forward
 
 dev = torch.device("cuda:0")
 kernel = sys.argv[1] if len(sys.argv) > 1 else "auto"
+from bitdelta_b200 import _lib
+_lib.lib.bd_debug_set_flags(int(os.environ.get("BD_DBG_FLAGS", "0")), int(os.environ.get("BD_LOAD_GROUP", "1")))
 shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [
     (6, 1, 4096, 4096), (6, 1, 4096, 1024), (6, 1, 4096, 14336), (6, 1, 14336, 4096),
     (1, 1, 4096, 4096), (1, 1, 4096, 14336), (1, 16, 4096, 4096), (1, 128, 4096, 4096), (3, 1, 4096, 14336)]
@@ -41,7 +43,7 @@ for (T, m, K, N) in shapes:
         e1.record(s)
         torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (5 * reps)
-    rec = {"kernel": kernel, "T": T, "m": m, "K": K, "N": N, "us": round(us, 2), "GBps": round(bytes_alg / us / 1e3, 1),
+    rec = {"kernel": kernel, "flags": os.environ.get("BD_DBG_FLAGS", "0"), "group": os.environ.get("BD_LOAD_GROUP", "default"), "T": T, "m": m, "K": K, "N": N, "us": round(us, 2), "GBps": round(bytes_alg / us / 1e3, 1),
            "frac_of_6574": round(bytes_alg / us / 1e3 / 6574.1, 3), "tflops": round(4 * T * m * N * K / us / 1e6, 2)}
     print(json.dumps(rec), flush=True)
     out.append(rec)

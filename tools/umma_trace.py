@@ -22,13 +22,13 @@ torch.cuda.synchronize()
 _lib.lib.bd_debug_set_trace(None)
 t = buf.cpu().view(64, 16)
 t0 = t[0, 8].item()
-names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty"]
+names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived"]
 print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
 print("unit " + " ".join(n.rjust(9) for n in names) + "   | unpack  mma_issue  afull->aempty(+2)")
 for it in range(64):
     if t[it, 0].item() == 0:
         break
-    row = [t[it, s].item() - t0 for s in range(9)]
+    row = [t[it, s].item() - t0 for s in range(12)]
     extra = ""
     if it + 2 < 64 and t[it + 2, 1].item():
         extra = f"{row[4]-row[1]:8d} {row[7]-row[6]:9d} {t[it+2,1].item()-t0-row[6]:9d}"
