@@ -113,8 +113,8 @@ BD_API int bd_select_kernel(int dtype, int64_t T, int64_t m, int64_t K, int64_t 
 /* Bring-up instrumentation: device buffer of 64 x 16 int64 clock64 stamps written by CTA 0 of the tcgen05 kernel
  * (per work unit: barrier waits, unpack, MMA issue); NULL disables it.  Not used by the Python surface. */
 BD_API void bd_debug_set_trace(void* device_buffer);
-/* Bring-up knobs of the tcgen05 kernel: flags bit 0 = stream operands only (no unpack/MMA/epilogue, outputs undefined);
- * load_group > 0 sets how many consecutive units the TMA producer issues back to back. */
+/* Bring-up knobs of the tcgen05 kernel: flags bit 0 = stream operands only (no unpack/MMA/epilogue, outputs undefined),
+ * bit 1 = force the 16-bit delta path; the second argument is reserved. */
 BD_API void bd_debug_set_flags(int flags, int load_group);
 
 #ifdef __cplusplus

@@ -398,8 +398,8 @@ def test_register_and_unregister_diff_compress():
     for t in range(T):
         h = torch.nn.functional.layer_norm(x[t].float(), (64,), ref_ckpts[t]["block.norm.weight"].float()).bfloat16()
         signs = bd.unpack(ref_ckpts[t]["block.q_proj.mask"]).double() * 2 - 1
-        exact = h.double() @ model.block.q_proj.weight.double().T + 0.01 * (h.double() @ signs)
-        assert_close_to_exact(y[t], exact.cpu().numpy(), f"tenant {t}")
+        exact = h.double() @ model.block.q_proj.weight.detach().double().T + 0.01 * (h.double() @ signs)
+        assert_close_to_exact(y[t].detach(), exact.cpu().numpy(), f"tenant {t}")
     bd.demo_backend.cached_modules.clear()
 
 

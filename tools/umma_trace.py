@@ -15,13 +15,27 @@ coeff = torch.full((T,), 0.002, device=dev)
 x = torch.randn(T, m, K, generator=g, device=dev).bfloat16()
 for _ in range(3):
     _fused_forward(x, w, ms, coeff, T, "umma")
-buf = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(64 * 16 + 4 * 160, dtype=torch.int64, device=dev)
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 _lib.lib.bd_debug_set_trace(buf.data_ptr())
 _fused_forward(x, w, ms, coeff, T, "umma")
+ev0.record()
+_fused_forward(x, w, ms, coeff, T, "umma")
+ev1.record()
 torch.cuda.synchronize()
+print(f"event time of one traced launch: {ev0.elapsed_time(ev1)*1e3:.1f} us")
 _lib.lib.bd_debug_set_trace(None)
-t = buf.cpu().view(64, 16)
+allt = buf.cpu()
+life = allt[1024:].view(160, 4)
+live = life[life[:, 0] > 0]
+e0 = live[:, 0].min().item()
+ent = (live[:, 0] - e0).float() / 1e3
+ex = (live[:, 1] - e0).float() / 1e3
+print(f"grid: {live.shape[0]} CTAs; entry us min/median/max = {ent.min():.2f}/{ent.median():.2f}/{ent.max():.2f}; exit us min/median/max = {ex.min():.2f}/{ex.median():.2f}/{ex.max():.2f}; lifetime median {(ex-ent).median():.2f} max {(ex-ent).max():.2f}")
+t = allt[:1024].view(64, 16)
 t0 = t[0, 8].item()
+k = t[63]
+print(f"kernel (CTA 0): entry->setup {k[1]-k[0]} cyc, setup->first TMA {t0-k[1]}, first TMA->last unit done {k[2]-t0}, last epilogue {k[3]-k[2]}, ->teardown {k[4]-k[3]}; total {k[4]-k[0]} cyc = {(k[9]-k[8])/1e3:.2f} us (globaltimer)")
 names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived"]
 print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
 print("unit " + " ".join(n.rjust(9) for n in names) + "   | unpack  mma_issue  afull->aempty(+2)")
