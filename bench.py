@@ -298,6 +298,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         cfg["kernel"] = kernel
         if layers != LAYERS:
             cfg["workload"] += f"_{layers}layers_DEBUG"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            except Exception:
+                traffic = None
         line = {
             "metric": "tokens/sec Mistral-7B+6delta batched decode (BinaryDiff linears)",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -307,7 +314,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "h2d_bytes_per_step": sum(t.numel() * 2 for t in host_in), "d2h_bytes_per_step": host_out.numel() * 2},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": f"bd fused forward ({kernel})",
+                         "traffic": traffic, "algorithmic_bytes_per_launch_avg": bytes_step / max(launches_per_step, 1), "peak_kind": peak_kind, "kernel": f"bd fused forward ({kernel})",
                          "algorithmic_bytes_per_step": bytes_step, "launches_per_step": launches_per_step,
                          "w1a16_tflops": step_flops(TENANTS, 1, layers) / (ms_step * 1e-3) / 1e12,
                          "w1a16_frac_of_bf16_peak": step_flops(TENANTS, 1, layers) / (ms_step * 1e-3) / 1e12 / tf_peak},

@@ -15,6 +15,7 @@ from .demo_backend import (
     unregister_diff_compress,
 )
 from .diff import BinaryDiff, compress_diff, fold_into, load_diff, save_diff, save_full_model
+from . import parallel  # noqa: F401
 
 __all__ = [
     "pack", "unpack", "binary_matmul", "binary_bmm",
