@@ -3,7 +3,8 @@
 
 A "step" is one decode step's worth of the hot path: all 224 BinaryDiff linears of Mistral-7B (32 layers x
 q/k/v/o/gate/up/down) evaluated for 6 tenants x 1 new token through `DiffCompressModule.forward`
-(demo/demo_backend.py:93-98 semantics), i.e. 224 launches of the fused kernel reading 13.96 GB of bf16 base weights and
+(demo/demo_backend.py:93-98 semantics): q/k/v and gate/up, which a decoder layer calls back to back on the same hidden
+states, share one launch (128 launches per step; --no-group gives 224), reading 13.96 GB of bf16 base weights and
 6 x 0.87 GB of sign words.  Attention, norms and the per-tenant lm_heads are not part of the W1A16 path and are not
 executed; the config says so.  Weights are random-init, inputs synthetic.
 
@@ -166,7 +167,7 @@ def workload_config(world: int):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def build_model(torch, bd, dev, layers: int, seed: int):
+def build_model(torch, bd, dev, layers: int, seed: int, grouped: bool = True):
     """Random-init Mistral-7B-shaped stack of DiffCompressModules on `dev`."""
     gen = torch.Generator(device=dev).manual_seed(seed)
     mods = []
@@ -179,6 +180,11 @@ def build_model(torch, bd, dev, layers: int, seed: int):
             masks = torch.randint(-(2**31), 2**31 - 1, (TENANTS, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
             coeffs = (torch.rand(TENANTS, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
             layer[name] = bd.DiffCompressModule(lin, masks, coeffs)
+        if grouped:
+            # what bd.fuse_sibling_projections does on a real decoder layer: projections the layer calls back to back on
+            # the same hidden states share one launch
+            bd.group_projections([layer["q_proj"], layer["k_proj"], layer["v_proj"]])
+            bd.group_projections([layer["gate_proj"], layer["up_proj"]])
         mods.append(layer)
     return mods
 
@@ -201,7 +207,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
 
     layers = args.layers
-    mods = build_model(torch, bd, dev, layers, seed=1234 + rank)
+    mods = build_model(torch, bd, dev, layers, seed=1234 + rank, grouped=not args.no_group)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     # static synthetic activations (one new token per tenant); outputs are not chained because the omitted norms
     # would be needed to keep magnitudes bounded
@@ -296,6 +302,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "sample": f"1 of {LAYERS} decoder layers (7 linears x {TENANTS} tenants x 1 token), best of 2, scaled x{LAYERS}"}
         cfg = workload_config(world)
         cfg["kernel"] = kernel
+        cfg["grouped_launches"] = "q/k/v and gate/up share a launch (SiblingGroup)" if not args.no_group else "off"
         if layers != LAYERS:
             cfg["workload"] += f"_{layers}layers_DEBUG"
         traffic = None
@@ -335,6 +342,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers (the result is labelled DEBUG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="one launch per linear (no q/k/v and gate/up grouping)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

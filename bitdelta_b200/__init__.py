@@ -11,6 +11,8 @@ from .demo_backend import (
     DataParallelModule,
     DiffCompress,
     DiffCompressModule,
+    fuse_sibling_projections,
+    group_projections,
     register_diff_compress,
     unregister_diff_compress,
 )
@@ -20,5 +22,5 @@ from . import parallel  # noqa: F401
 __all__ = [
     "pack", "unpack", "binary_matmul", "binary_bmm",
     "BinaryDiff", "compress_diff", "save_diff", "load_diff", "save_full_model", "fold_into",
-    "DiffCompressModule", "DataParallelModule", "register_diff_compress", "unregister_diff_compress", "DiffCompress",
+    "DiffCompressModule", "DataParallelModule", "register_diff_compress", "unregister_diff_compress", "DiffCompress", "group_projections", "fuse_sibling_projections",
 ]

@@ -23,7 +23,7 @@ EXPORTS = [
     "bd_abi_version", "bd_last_error", "bd_launch_count",
     "bd_pack", "bd_unpack", "bd_pack_host", "bd_unpack_host",
     "bd_compress", "bd_fold",
-    "bd_binary_bmm", "bd_binarydiff_fwd_batched",
+    "bd_binary_bmm", "bd_binarydiff_fwd_batched", "bd_binarydiff_fwd_grouped",
     "bd_workspace_bytes", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags",
 ]
 
@@ -52,6 +52,7 @@ def _load() -> ctypes.CDLL:
     lib.bd_fold.argtypes = [vp, vp, vp, i32, i64, i64, vp]
     lib.bd_binary_bmm.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i64, vp, sz, i32, vp]
     lib.bd_binarydiff_fwd_batched.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, i64, i64, vp, sz, i32, vp]
+    lib.bd_binarydiff_fwd_grouped.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i64, i64, i64, vp, sz, i32, vp]
     lib.bd_workspace_bytes.argtypes = [i64, i64]
     lib.bd_workspace_bytes.restype = sz
     lib.bd_select_kernel.argtypes = [i32, i64, i64, i64, i64, i32]

@@ -88,6 +88,43 @@ extern "C" BD_API int bd_binary_bmm(const void* a, const int32_t* words, void* c
   return dispatch(p, kernel, "bd_binary_bmm");
 }
 
+extern "C" BD_API int bd_binarydiff_fwd_grouped(const void* x, int nseg, const void* const* w, const int32_t* const* masks, const void* const* coeff,
+                                                 int coeff_dtype, void* const* y, const int64_t* N, const int64_t* mask_tenant_stride, int dtype,
+                                                 int64_t T, int64_t m, int64_t K, void* workspace, size_t workspace_bytes, int kernel,
+                                                 void* stream) {
+  if (nseg < 1 || nseg > 3) return fail(BD_ERR_INVALID, "bd_binarydiff_fwd_grouped: nseg must be 1..3 (got %d)", nseg);
+  if (!w || !masks || !coeff || !y || !N || !mask_tenant_stride) return fail(BD_ERR_INVALID, "bd_binarydiff_fwd_grouped: null pointer array");
+  FwdProblem segs[3];
+  for (int sg = 0; sg < nseg; ++sg) {
+    FwdProblem& p = segs[sg];
+    p = FwdProblem{};
+    if (!w[sg]) return fail(BD_ERR_INVALID, "bd_binarydiff_fwd_grouped: w[%d] is required", sg);
+    p.x = x; p.w = w[sg]; p.masks = masks[sg]; p.coeff = coeff[sg]; p.coeff_dtype = coeff_dtype; p.y = y[sg]; p.dtype = dtype;
+    p.T = T; p.m = m; p.K = K; p.N = N[sg]; p.mask_tenant_stride = mask_tenant_stride[sg];
+    p.workspace = workspace; p.workspace_bytes = workspace_bytes; p.stream = (cudaStream_t)stream;
+    int rc = validate(p, "bd_binarydiff_fwd_grouped");
+    if (rc) return rc;
+  }
+  const char* why = "";
+  bool umma_ok = kernel != BD_KERNEL_SIMT;
+  for (int sg = 0; sg < nseg && umma_ok; ++sg) umma_ok = umma_supports(segs[sg], &why);
+  if (kernel == BD_KERNEL_UMMA && !umma_ok) return fail(BD_ERR_UNSUPPORTED, "bd_binarydiff_fwd_grouped: tcgen05 kernel does not support this problem: %s", why);
+  if (umma_ok) {
+    FwdProblem g = segs[0];
+    g.nseg = nseg;
+    for (int sg = 1; sg < nseg; ++sg) {
+      g.seg_w[sg - 1] = segs[sg].w; g.seg_masks[sg - 1] = segs[sg].masks; g.seg_coeff[sg - 1] = segs[sg].coeff; g.seg_y[sg - 1] = segs[sg].y;
+      g.seg_N[sg - 1] = segs[sg].N; g.seg_mask_tenant_stride[sg - 1] = segs[sg].mask_tenant_stride;
+    }
+    return launch_fwd_umma(g);
+  }
+  for (int sg = 0; sg < nseg; ++sg) {  // general kernel: one launch per matrix
+    int rc = launch_fwd_simt(segs[sg]);
+    if (rc) return rc;
+  }
+  return BD_OK;
+}
+
 extern "C" BD_API int bd_binarydiff_fwd_batched(const void* x, const void* w, const int32_t* masks, const void* coeff, int coeff_dtype, void* y,
                                          int dtype, int64_t T, int64_t m, int64_t K, int64_t N, int64_t mask_tenant_stride,
                                          void* workspace, size_t workspace_bytes, int kernel, void* stream) {

@@ -83,6 +83,15 @@ struct FwdProblem {
   void* workspace;
   size_t workspace_bytes;
   cudaStream_t stream;
+  // Grouped launch (optional): `nseg` > 1 matrices that share x, K, T, m -- e.g. q/k/v or gate/up.  Segment 0 is the
+  // main w/masks/coeff/y/N above; segments 1.. are listed here.  Every N but the last must be a multiple of 128.
+  int nseg = 1;
+  const void* seg_w[2] = {nullptr, nullptr};
+  const int32_t* seg_masks[2] = {nullptr, nullptr};
+  const void* seg_coeff[2] = {nullptr, nullptr};
+  void* seg_y[2] = {nullptr, nullptr};
+  int64_t seg_N[2] = {0, 0};
+  int64_t seg_mask_tenant_stride[2] = {0, 0};
 };
 
 // Workspace layout shared by the forward kernels: two zero-initialised counter regions, then scratch.

@@ -137,23 +137,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] . B[smem desc]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -181,27 +164,28 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   return __uint_as_float(r);
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 in bits [46,48), layout type 2 in
-// bits [61,64)); rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
-  d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset
-  d |= (uint64_t)1 << 46;                        // descriptor version
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
 // kind::f16 instruction descriptor: fp32 accumulate, K-major A and B, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 = f16, 1 = bf16*/, int n) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------- kernel
+constexpr int kMaxSeg = 3;  // matrices sharing one activation block in one launch (q/k/v, gate/up)
+
+struct UmmaMaps {
+  CUtensorMap w[kMaxSeg], m[kMaxSeg], x;
+};
+
 struct UmmaArgs {
-  const void* coeff;
+  const void* coeff;   // segment 0 (kept for the single-matrix case)
   int coeff_dtype;
   void* y;
+  // grouped launch: segment s owns tiles [seg_tile0[s], seg_tile0[s+1]) and writes y_seg[s] ([rows, n_seg[s]])
+  int nseg;
+  int seg_tile0[kMaxSeg + 1];
+  int n_seg[kMaxSeg];
+  void* y_seg[kMaxSeg];
+  const void* coeff_seg[kMaxSeg];
   float* partial;     // [grid][2][rows][128]
   unsigned* counters; // [n_tiles]
   int T, m, rows;     // tenants, rows per tenant, T*m
@@ -308,8 +292,8 @@ __host__ __device__ constexpr uint32_t make_idesc8(int n) {
 
 template <typename T16, bool HAS_BASE, bool DELTA8, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
-fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_m,
-                const __grid_constant__ CUtensorMap tmap_x, const UmmaArgs a) {
+fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
+  const CUtensorMap& tmap_x = maps.x;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles and their UMMA descriptors need 1024-byte alignment: align by hand (the host adds 1 KiB of slack)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -341,8 +325,10 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 
   // ---- one-time setup ----
   if (warp == kWarpProducer && lane == 0) {
-    if (HAS_BASE) prefetch_tmap(&tmap_w);
-    prefetch_tmap(&tmap_m);
+    for (int sg = 0; sg < a.nseg; ++sg) {
+      if (HAS_BASE) prefetch_tmap(&maps.w[sg]);
+      prefetch_tmap(&maps.m[sg]);
+    }
     prefetch_tmap(&tmap_x);
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -442,8 +428,10 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         for (int i = 0; i < npre; ++i) {
           uint8_t* sp = smem + (size_t)i * a.stage_bytes;
           mbar_arrive_expect_tx(&bar_full[i], a.tx_bytes);
-          if (HAS_BASE) tma_load_2d(sp, &tmap_w, &bar_full[i], k2 * kBlockK, t2 * kTileN, kEvictFirst);
-          tma_load_3d(sp + a.off_masks, &tmap_m, &bar_full[i], t2 * kTileN, k2 * (kBlockK / 32), 0, kEvictFirst);
+          const int sg = (t2 >= a.seg_tile0[1]) + (t2 >= a.seg_tile0[2]);
+          const int lt = t2 - a.seg_tile0[sg];
+          if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[i], k2 * kBlockK, lt * kTileN, kEvictFirst);
+          tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[i], lt * kTileN, k2 * (kBlockK / 32), 0, kEvictFirst);
           if (++k2 == a.kblocks) { k2 = 0; ++t2; }
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -460,8 +448,10 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         trace_mark<TRACE>(a, u - u_begin, 8);
         uint8_t* sp = smem + (size_t)st.idx * a.stage_bytes;
         mbar_arrive_expect_tx(&bar_full[st.idx], a.tx_bytes);
-        if (HAS_BASE) tma_load_2d(sp, &tmap_w, &bar_full[st.idx], kb * kBlockK, tile * kTileN, kEvictFirst);
-        tma_load_3d(sp + a.off_masks, &tmap_m, &bar_full[st.idx], tile * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
+        const int sg = (tile >= a.seg_tile0[1]) + (tile >= a.seg_tile0[2]);
+        const int lt = tile - a.seg_tile0[sg];
+        if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[st.idx], kb * kBlockK, lt * kTileN, kEvictFirst);
+        tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[st.idx], lt * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
         tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], kb * kBlockK, 0, kEvictLast);
         st.advance(a.stages);
         if (++kb == a.kblocks) { kb = 0; ++tile; }
@@ -578,7 +568,6 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     const int ut = threadIdx.x;         // 0..255
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     constexpr uint32_t kOne = DELTA8 ? 0x38383838u : (std::is_same<T16, __nv_bfloat16>::value ? 0x3F803F80u : 0x3C003C00u);
-    T16* __restrict__ y = reinterpret_cast<T16*>(a.y);
     uint32_t sign_mask = DELTA8 ? 0x80808080u : 0x80008000u;
     asm volatile("" : "+r"(sign_mask));  // keep the mask in a register so mask + constant fit one LOP3
     Ring st, ab;
@@ -686,7 +675,13 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         dphase ^= 1u;
         tc_fence_after();
         const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
-        const int64_t n = (int64_t)tile * kTileN + row;
+        // which matrix of a grouped launch this tile belongs to
+        const int sg = (tile >= a.seg_tile0[1]) + (tile >= a.seg_tile0[2]);
+        const int ltile = tile - a.seg_tile0[sg];
+        const int64_t seg_n = a.n_seg[sg];
+        T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
+        const void* seg_coeff = a.coeff_seg[sg];
+        const int64_t n = (int64_t)ltile * kTileN + row;
         // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run
         // of a CTA can be partial; the runs in between cover whole tiles)
         const int slot = seg_is_first ? 0 : 1;
@@ -696,7 +691,7 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           // delta accumulator: 16 columns per tenant, column 3i+p = piece p of row i (m <= 5); the two warps of a
           // quadrant take alternate tenants
           for (int t = grp; t < a.T; t += 2) {
-            const float cf = HAS_BASE ? load_coeff(a.coeff, a.coeff_dtype, t) : 1.0f;
+            const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
             float d0[8], d1[8], bv[5];
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16, d0);
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16 + 8, d1);
@@ -714,7 +709,7 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               const int r = t * a.m + i;
               const float v = HAS_BASE ? fmaf(cf, dsum[i], bv[i]) : dsum[i];
               if (full_k) {
-                if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+                if (n < seg_n) y[(int64_t)r * seg_n + n] = F16<T16>::from_f32(v);
               } else {
                 part[(size_t)r * kTileN + row] = v;
               }
@@ -722,7 +717,7 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           }
         } else
         for (int t = 0; t < a.T; ++t) {
-          const float cf = HAS_BASE ? load_coeff(a.coeff, a.coeff_dtype, t) : 1.0f;
+          const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
           for (int c8 = 0; c8 < a.mp / 8; ++c8) {
             if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
             if (c8 * 8 >= a.m) continue;
@@ -741,7 +736,7 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               const int r = t * a.m + ii;
               const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
               if (full_k) {
-                if (n < a.N) y[(int64_t)r * a.N + n] = F16<T16>::from_f32(v);
+                if (n < seg_n) y[(int64_t)r * seg_n + n] = F16<T16>::from_f32(v);
               } else {
                 part[(size_t)r * kTileN + row] = v;
               }
@@ -786,9 +781,9 @@ fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
               }
-              const int64_t n4 = (int64_t)tile * kTileN + q4 * 4;
-              T16* dst = y + (int64_t)r * a.N + n4;
-              if (n4 + 3 < a.N) {  // N % 4 == 0 and rows of y are 8-byte aligned for these 4 elements
+              const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
+              T16* dst = y + (int64_t)r * seg_n + n4;
+              if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte aligned for these 4 elements
                 const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
                 *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
               }
@@ -924,8 +919,7 @@ int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* b
 }
 
 template <typename T16, bool HAS_BASE, bool DELTA8, bool TRACE>
-int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const CUtensorMap& tw, const CUtensorMap& tm, const CUtensorMap& tx, const UmmaArgs& args,
-                 int grid) {
+int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const UmmaMaps& maps, const UmmaArgs& args, int grid) {
   auto kern = fwd_umma_kernel<T16, HAS_BASE, DELTA8, TRACE>;
   static std::once_flag once;  // one per template instantiation
   static cudaError_t attr_err = cudaSuccess;
@@ -941,7 +935,7 @@ int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const CUtensorMap& t
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tw, tm, tx, args);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, args);
   if (le != cudaSuccess) return fail(BD_ERR_CUDA, "cudaLaunchKernelEx(fwd_umma_kernel) failed: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("fwd_umma_kernel");
@@ -979,10 +973,24 @@ size_t umma_workspace_bytes(int64_t rows, int64_t N) {
 
 static int launch_one(const FwdProblem& p) {
   int64_t T = p.T, m = p.m;
-  int64_t tenant_stride = p.mask_tenant_stride;
-  if (tenant_stride == 0) tenant_stride = (p.K / 32) * p.N;
   const bool has_base = p.w != nullptr;
-  UmmaPlan plan = choose_plan(p.dtype, T, m, p.K, p.N, has_base);
+  const int nseg = p.nseg < 1 ? 1 : p.nseg;
+  if (nseg > kMaxSeg) return fail(BD_ERR_INVALID, "tcgen05 kernel: at most %d matrices per grouped launch", kMaxSeg);
+  // per-segment views
+  const void* ws[kMaxSeg] = {p.w, p.seg_w[0], p.seg_w[1]};
+  const int32_t* ms[kMaxSeg] = {p.masks, p.seg_masks[0], p.seg_masks[1]};
+  const void* cs[kMaxSeg] = {p.coeff, p.seg_coeff[0], p.seg_coeff[1]};
+  void* ys[kMaxSeg] = {p.y, p.seg_y[0], p.seg_y[1]};
+  int64_t Ns[kMaxSeg] = {p.N, p.seg_N[0], p.seg_N[1]};
+  int64_t strides[kMaxSeg] = {p.mask_tenant_stride, p.seg_mask_tenant_stride[0], p.seg_mask_tenant_stride[1]};
+  int64_t n_max = 0;
+  for (int sg = 0; sg < nseg; ++sg) {
+    if (strides[sg] == 0) strides[sg] = (p.K / 32) * Ns[sg];
+    if (sg + 1 < nseg && Ns[sg] % kTileN != 0) return fail(BD_ERR_UNSUPPORTED, "grouped launch: every N but the last must be a multiple of %d", kTileN);
+    if (Ns[sg] % 4 != 0) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: N must be a multiple of 4");
+    if (Ns[sg] > n_max) n_max = Ns[sg];
+  }
+  UmmaPlan plan = choose_plan(p.dtype, T, m, p.K, n_max, has_base);
   if (!plan.ok) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: %s", plan.why);
   DeviceInfo di = device_info();
   if (di.cc_major != 10) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel needs an sm_100 device (found compute capability %d.x)", di.cc_major);
@@ -995,7 +1003,18 @@ static int launch_one(const FwdProblem& p) {
   a.T = (int)T; a.m = (int)m; a.rows = (int)rows; a.inv_m = (uint32_t)((65536 + m - 1) / m); a.mp = plan.mp; a.ntb = plan.ntb;
   a.K = (int)p.K; a.N = (int)p.N;
   a.kblocks = (int)((p.K + kBlockK - 1) / kBlockK);
-  a.n_tiles = (int)((p.N + kTileN - 1) / kTileN);
+  a.nseg = nseg;
+  int tiles = 0;
+  for (int sg = 0; sg <= kMaxSeg; ++sg) a.seg_tile0[sg] = 0x7fffffff;  // unused segments never match
+  for (int sg = 0; sg < nseg; ++sg) {
+    a.seg_tile0[sg] = tiles;
+    a.n_seg[sg] = (int)Ns[sg];
+    a.y_seg[sg] = ys[sg];
+    a.coeff_seg[sg] = cs[sg];
+    tiles += (int)((Ns[sg] + kTileN - 1) / kTileN);
+  }
+  if (tiles > (int)(kWsCounterBytes / sizeof(unsigned))) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: too many N tiles");
+  a.n_tiles = tiles;
   a.total_units = a.n_tiles * a.kblocks;
   const int grid = a.total_units < di.sms ? a.total_units : di.sms;
   a.units_per_cta = a.total_units / grid;
@@ -1012,35 +1031,36 @@ static int launch_one(const FwdProblem& p) {
   a.dbg_flags = g_dbg_flags;
 
   const CUtensorMapDataType dt16 = p.dtype == BD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  alignas(64) CUtensorMap tw{}, tm{}, tx{};
+  alignas(64) UmmaMaps maps{};
   int rc;
-  if (has_base) {
-    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N}, str[1] = {(cuuint64_t)p.K * 2};
-    cuuint32_t box[2] = {kBlockK, kTileN};
-    if ((rc = encode_map(&tw, dt16, 2, p.w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
-  }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)(p.K / 32), (cuuint64_t)T};
-    cuuint64_t str[2] = {(cuuint64_t)p.N * 4, (cuuint64_t)tenant_stride * 4};
+  for (int sg = 0; sg < nseg; ++sg) {
+    if (has_base) {
+      if (!ws[sg]) return fail(BD_ERR_INVALID, "grouped launch: segment %d has no base weight", sg);
+      cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)Ns[sg]}, str[1] = {(cuuint64_t)p.K * 2};
+      cuuint32_t box[2] = {kBlockK, kTileN};
+      if ((rc = encode_map(&maps.w[sg], dt16, 2, ws[sg], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)Ns[sg], (cuuint64_t)(p.K / 32), (cuuint64_t)T};
+    cuuint64_t str[2] = {(cuuint64_t)Ns[sg] * 4, (cuuint64_t)strides[sg] * 4};
     cuuint32_t box[3] = {kTileN, kBlockK / 32, (cuuint32_t)T};
-    if ((rc = encode_map(&tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, p.masks, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "masks"))) return rc;
+    if ((rc = encode_map(&maps.m[sg], CU_TENSOR_MAP_DATA_TYPE_INT32, 3, ms[sg], dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "masks"))) return rc;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)rows}, str[1] = {(cuuint64_t)p.K * 2};
     cuuint32_t box[2] = {kBlockK, (cuuint32_t)plan.ntb};
-    if ((rc = encode_map(&tx, dt16, 2, p.x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
+    if ((rc = encode_map(&maps.x, dt16, 2, p.x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
   }
   if (p.dtype == BD_BF16) {
     if (plan.d8) {
-      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, true>(p, plan, tw, tm, tx, a, grid);  // instrumented build
-      return has_base ? launch_typed<__nv_bfloat16, true, true, false>(p, plan, tw, tm, tx, a, grid)
-                      : launch_typed<__nv_bfloat16, false, true, false>(p, plan, tw, tm, tx, a, grid);
+      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, true>(p, plan, maps, a, grid);  // instrumented build
+      return has_base ? launch_typed<__nv_bfloat16, true, true, false>(p, plan, maps, a, grid)
+                      : launch_typed<__nv_bfloat16, false, true, false>(p, plan, maps, a, grid);
     }
-    return has_base ? launch_typed<__nv_bfloat16, true, false, false>(p, plan, tw, tm, tx, a, grid)
-                    : launch_typed<__nv_bfloat16, false, false, false>(p, plan, tw, tm, tx, a, grid);
+    return has_base ? launch_typed<__nv_bfloat16, true, false, false>(p, plan, maps, a, grid)
+                    : launch_typed<__nv_bfloat16, false, false, false>(p, plan, maps, a, grid);
   }
-  return has_base ? launch_typed<__half, true, false, false>(p, plan, tw, tm, tx, a, grid)
-                  : launch_typed<__half, false, false, false>(p, plan, tw, tm, tx, a, grid);
+  return has_base ? launch_typed<__half, true, false, false>(p, plan, maps, a, grid)
+                  : launch_typed<__half, false, false, false>(p, plan, maps, a, grid);
 }
 
 void umma_set_trace(long long* buf) { g_trace_buf = buf; }
@@ -1054,6 +1074,25 @@ int launch_fwd_umma(const FwdProblem& p0) {
   const size_t esz = 2;  // bf16 / fp16
   const size_t csz = p.coeff_dtype == BD_FP32 ? 4 : 2;
   const bool has_base = p.w != nullptr;
+  if (p.nseg > 1) {
+    int64_t n_max = p.N;
+    for (int sg = 1; sg < p.nseg; ++sg) n_max = p.seg_N[sg - 1] > n_max ? p.seg_N[sg - 1] : n_max;
+    bool aligned = p.N % kTileN == 0;
+    for (int sg = 1; sg + 1 < p.nseg; ++sg) aligned = aligned && (p.seg_N[sg - 1] % kTileN == 0);
+    if (aligned && choose_plan(p.dtype, p.T, p.m, p.K, n_max, has_base).ok) return launch_one(p);
+    // does not fit one grouped launch: run the matrices one by one
+    FwdProblem s = p;
+    s.nseg = 1;
+    int rc = launch_fwd_umma(s);
+    for (int sg = 1; sg < p.nseg && rc == BD_OK; ++sg) {
+      s = p;
+      s.nseg = 1;
+      s.w = p.seg_w[sg - 1]; s.masks = p.seg_masks[sg - 1]; s.coeff = p.seg_coeff[sg - 1]; s.y = p.seg_y[sg - 1];
+      s.N = p.seg_N[sg - 1]; s.mask_tenant_stride = p.seg_mask_tenant_stride[sg - 1];
+      rc = launch_fwd_umma(s);
+    }
+    return rc;
+  }
   if (choose_plan(p.dtype, p.T, p.m, p.K, p.N, has_base).ok) return launch_one(p);
   if (p.T > 1) {
     int g = p.m <= 16 ? tenants_per_launch(p.dtype, p.T, p.m, p.K, p.N, has_base) : 1;

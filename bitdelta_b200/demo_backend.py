@@ -17,7 +17,7 @@ import gc
 import torch
 import torch.nn as nn
 
-from .diff import _fused_forward
+from .diff import _fused_forward, _fused_forward_grouped
 
 
 class DataParallelModule(nn.Module):
@@ -47,10 +47,64 @@ class DataParallelModule(nn.Module):
         return out
 
 
+class SiblingGroup:
+    """DiffCompressModules that are always called back to back on the SAME input (q/k/v of an attention block, gate/up of an
+    MLP -- exactly how the HF decoder layer calls them).  The first call of a round launches ONE grouped kernel for all
+    members; the other members' calls return their cached output.  A member called with a different input (or twice)
+    simply triggers a new launch, so results never depend on the caller following the pattern."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        self._key = None
+        self._x = None  # keeps the activations alive while outputs are cached, so the key cannot be recycled
+        self._outs = {}
+
+    def forward_for(self, who, x):
+        key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, x.device)
+        if self._key != key or id(who) not in self._outs:
+            T = who.mask.shape[0]
+            ws = [m.module.weight if m.module.weight.is_contiguous() else m.module.weight.contiguous() for m in self.members]
+            ys = _fused_forward_grouped(x, ws, [m.mask for m in self.members], [m.coeff for m in self.members], T, who.kernel)
+            self._key, self._x = key, x
+            self._outs = {id(m): y for m, y in zip(self.members, ys)}
+        y = self._outs.pop(id(who))
+        if not self._outs:
+            self._key, self._x = None, None
+        return y
+
+
+def group_projections(members):
+    """Make `members` (DiffCompressModules with the same input features and tenants) share one grouped launch."""
+    members = list(members)
+    assert all(isinstance(m, DiffCompressModule) for m in members) and 2 <= len(members) <= 3
+    K = members[0].module.weight.shape[1]
+    assert all(m.module.weight.shape[1] == K and m.mask.shape[0] == members[0].mask.shape[0] for m in members)
+    assert all(getattr(m.module, "bias", None) is None for m in members), "grouped launch supports bias-free linears"
+    g = SiblingGroup(members)
+    for m in members:
+        m._group = g
+    return g
+
+
+def fuse_sibling_projections(model):
+    """Opt-in: group q_proj/k_proj/v_proj and gate_proj/up_proj DiffCompressModules that share a parent (after
+    register_diff_compress).  The HF decoder layer calls them one after the other on the same hidden states."""
+    n = 0
+    for _, parent in model.named_modules():
+        kids = dict(parent.named_children())
+        for names in (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")):
+            mods = [kids.get(nm) for nm in names]
+            if all(isinstance(mm, DiffCompressModule) for mm in mods) and getattr(mods[0], "_group", None) is None:
+                group_projections(mods)
+                n += 1
+    return n
+
+
 class DiffCompressModule(nn.Module):
     """Shared ``nn.Linear`` + per-tenant 1-bit deltas (:82-98): ``y[t] = module(x[t]) + coeff[t] * (x[t] . sign_t)``."""
 
     kernel = "auto"
+    _group = None  # set by group_projections / fuse_sibling_projections
 
     def __init__(self, module, mask_list, coeff_list):
         super().__init__()
@@ -63,6 +117,8 @@ class DiffCompressModule(nn.Module):
         T = self.mask.shape[0]
         assert hidden_states.dim() == 3 and hidden_states.shape[0] == T, "Incompatible batch dimensions"
         x = hidden_states.contiguous()
+        if self._group is not None and x.is_cuda:
+            return self._group.forward_for(self, x)
         w = self.module.weight
         if not w.is_contiguous():
             w = w.contiguous()
@@ -115,6 +171,7 @@ def unregister_diff_compress(model):
             parent = model.get_submodule(".".join(name.split(".")[:-1]))
             setattr(parent, name.split(".")[-1], module.module)
         elif isinstance(module, DiffCompressModule):
+            module._group = None
             parent = model.get_submodule(".".join(name.split(".")[:-1]))
             setattr(parent, name.split(".")[-1], module.module)
 

@@ -57,6 +57,46 @@ def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coe
     return y
 
 
+def _fused_forward_grouped(x: torch.Tensor, weights, masks_list, coeffs, T: int, kernel="auto"):
+    """Several BinaryDiff linears on the SAME activations in one launch (q/k/v, gate/up).  x: (T, m, K); weights[s]: (N_s, K);
+    masks_list[s]: (T, K/32, N_s) int32; coeffs[s]: (T,).  Returns [y_s (T, m, N_s)]."""
+    import ctypes
+
+    if not x.is_cuda:
+        raise RuntimeError(f"bitdelta_b200: grouped fused forward needs CUDA tensors (got {x.device}). There is no CPU fallback.")
+    nseg = len(weights)
+    assert 1 <= nseg <= 3 and len(masks_list) == nseg and len(coeffs) == nseg
+    m, K = x.shape[1], x.shape[2]
+    cdt = coeffs[0].dtype if coeffs[0].dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32
+    cs = []
+    for c in coeffs:
+        c = c.detach().to(cdt).reshape(-1)
+        if c.numel() == 1 and T > 1:
+            c = c.expand(T)
+        cs.append(c.contiguous())
+    ys, strides, Ns = [], [], []
+    for w, mk in zip(weights, masks_list):
+        assert w.is_contiguous() and w.shape[1] == K and w.dtype == x.dtype and mk.dtype == torch.int32 and mk.is_contiguous()
+        assert mk.shape[-2] * 32 == K and mk.shape[-1] == w.shape[0] and (mk.dim() == 2 or mk.shape[0] == T), "Incompatible dimensions"
+        Ns.append(w.shape[0])
+        strides.append(mk.shape[-2] * mk.shape[-1] if mk.dim() == 3 else 0)
+        ys.append(torch.empty((T, m, w.shape[0]), device=x.device, dtype=x.dtype))
+    if x.numel() == 0:
+        return ys
+    vp = ctypes.c_void_p
+    arr = lambda ts: (vp * nseg)(*[t.data_ptr() for t in ts])  # noqa: E731
+    i64 = lambda vs: (ctypes.c_int64 * nseg)(*vs)  # noqa: E731
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(x.device, T * m, max(Ns))
+        _lib.check(
+            _lib.lib.bd_binarydiff_fwd_grouped(
+                x.data_ptr(), nseg, arr(weights), arr(masks_list), arr(cs), _lib.dtype_code(cdt), arr(ys), i64(Ns), i64(strides),
+                _lib.dtype_code(x.dtype), T, m, K, ws.data_ptr(), ws.numel(), _lib.kernel_code(kernel), _lib.stream_ptr(x.device),
+            )
+        )
+    return ys
+
+
 class BinaryDiff(nn.Module):
     """16-bit base weight + 1-bit delta linear layer (reference ``BinaryDiff``, diff.py:8-39).
 

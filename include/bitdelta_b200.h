@@ -103,6 +103,16 @@ BD_API int bd_binarydiff_fwd_batched(const void* x, const void* w, const int32_t
                               int dtype, int64_t T, int64_t m, int64_t K, int64_t N, int64_t mask_tenant_stride,
                               void* workspace, size_t workspace_bytes, int kernel, void* stream);
 
+/* Grouped form: `nseg` (1..3) BinaryDiff linears that consume the SAME activations in one launch -- q/k/v of an attention
+ * block or gate/up of an MLP (the callers of a6/a7 in SURVEY.md 3.1/3.2 issue them back to back on one input).  Arrays
+ * have `nseg` entries: w[s] [N[s], K], masks[s] (tenant stride mask_tenant_stride[s] words), coeff[s] (T values),
+ * y[s] [T, m, N[s]].  Semantics per matrix are exactly bd_binarydiff_fwd_batched's; one launch streams all of them, so the
+ * per-launch fixed cost is paid once.  Every N but the last must be a multiple of 128 for the single-launch path
+ * (otherwise, or on the SIMT kernel, the matrices are processed one after the other). */
+BD_API int bd_binarydiff_fwd_grouped(const void* x, int nseg, const void* const* w, const int32_t* const* masks, const void* const* coeff,
+                              int coeff_dtype, void* const* y, const int64_t* N, const int64_t* mask_tenant_stride, int dtype,
+                              int64_t T, int64_t m, int64_t K, void* workspace, size_t workspace_bytes, int kernel, void* stream);
+
 /* Upper bound of the workspace any forward of at most `max_rows` = T*m rows and `max_n` outputs needs on the
  * current device. */
 BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n);

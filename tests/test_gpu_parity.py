@@ -333,6 +333,81 @@ def test_mistral_shapes_six_tenants(kernel, N, K, m, T):
     assert np.allclose(exact[:, :, sl].cpu().numpy(), ex_o, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("shapes,T,m", [([4096, 1024, 1024], 6, 1), ([14336, 14336], 6, 1), ([256, 384, 200], 3, 2), ([1024, 1024], 8, 1)])
+def test_grouped_launch_matches_individual_modules(shapes, T, m):
+    # q/k/v and gate/up called back to back on the same input share ONE launch (SiblingGroup); results must match the
+    # float64 truth like the individual launches do, and a member called on a different input must not see cached data
+    K = 4096 if shapes[0] >= 1024 else 512
+    gen = torch.Generator(device=DEV).manual_seed(sum(shapes) + T)
+    mods, exacts = [], []
+    x = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    x2 = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    for N in shapes:
+        lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+        with torch.no_grad():
+            lin.weight.normal_(0.0, 0.02, generator=gen)
+        masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+        coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.003 + 0.0005).bfloat16()
+        mods.append(bd.DiffCompressModule(lin, masks, coeffs))
+    def truth(mod, xin):
+        signs = bd.unpack(mod.mask).double() * 2 - 1
+        return (xin.double() @ mod.module.weight.detach().double().T + mod.coeff.double()[:, None, None] * torch.bmm(xin.double(), signs)).cpu().numpy()
+    singles = [mod(x) for mod in mods]
+    n0 = bd._lib.launch_count()
+    bd.group_projections(mods)
+    grouped = [mod(x) for mod in mods]
+    launches = bd._lib.launch_count() - n0
+    if all(N % 128 == 0 for N in shapes[:-1]) and T <= 6:
+        assert launches == 1, launches
+    for mod, yg, ys in zip(mods, grouped, singles):
+        assert_close_to_exact(yg, truth(mod, x), "grouped")
+        assert (yg.float() - ys.float()).abs().max() <= 2.0**-7 * ys.float().abs().max()  # at most an output ulp apart
+    # out-of-pattern use: only the second member, on another input -> fresh launch, correct result
+    y2 = mods[1](x2)
+    assert_close_to_exact(y2, truth(mods[1], x2), "grouped, different input")
+    y0 = mods[0](x)
+    assert_close_to_exact(y0, truth(mods[0], x), "grouped, first member again")
+
+
+def test_fuse_sibling_projections_on_a_decoder_like_block():
+    import torch.nn as nn
+
+    class Attn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = nn.Linear(256, 256, bias=False)
+            self.k_proj = nn.Linear(256, 128, bias=False)
+            self.v_proj = nn.Linear(256, 128, bias=False)
+            self.o_proj = nn.Linear(256, 256, bias=False)
+
+        def forward(self, x):
+            return self.o_proj(self.q_proj(x) + torch.cat([self.k_proj(x), self.v_proj(x)], dim=-1))
+
+    torch.manual_seed(0)
+    model = nn.Sequential()
+    model.add_module("self_attn", Attn())
+    model = model.to(DEV, torch.bfloat16)
+    T = 2
+    names = ["q_proj", "k_proj", "v_proj", "o_proj"]
+    ckpts = [{f"self_attn.{n}.mask": bd.pack(torch.rand(256, getattr(model.self_attn, n).out_features, device=DEV) > 0.5)
+              for n in names} for _ in range(T)]
+    for c in ckpts:
+        for n in names:
+            c[f"self_attn.{n}.coeff"] = torch.tensor(0.004, device=DEV)
+    bd.demo_backend.cached_modules.clear()
+    x = torch.randn(T, 3, 256, device=DEV).bfloat16()
+    with torch.no_grad():
+        bd.register_diff_compress(model, ckpts)
+        y_plain = model(x)
+        assert bd.fuse_sibling_projections(model) == 1
+        n0 = bd._lib.launch_count()
+        y_fused = model(x)
+        assert bd._lib.launch_count() - n0 == 2  # q/k/v in one launch + o_proj
+        bd.unregister_diff_compress(model)
+    assert (y_fused.float() - y_plain.float()).abs().max() <= 2.0**-6 * y_plain.float().abs().max()
+    bd.demo_backend.cached_modules.clear()
+
+
 def test_linearity_in_the_coefficient():
     # size-independent property at full size: y(2c) - y(c) == y(c) - y(0)  up to bf16 rounding
     T, N, K = 6, 4096, 4096
