@@ -195,7 +195,10 @@ struct UmmaArgs {
   int K, N;
   int kblocks;        // ceil(K / 64)
   int n_tiles;
-  int total_units, units_per_cta, units_rem;  // CTA c owns units [c*U + min(c,R), ...)
+  int total_units, units_per_cta, units_rem;  // CTA c owns units quantum * [c*U + min(c,R), ...)
+  int unit_quantum;   // 1 = stream-K over single units; kblocks = whole (tile, row chunk) runs per CTA (no split-K fix-up)
+  int m_chunks;       // row chunks of a.m rows each (prefill-size launches of one tenant); tile id = n_tile * m_chunks + chunk
+  int m_total;        // rows of the tenant over all chunks
   int stages;
   int n_abuf;         // TMEM A-operand buffers in use (2..kMaxABuf)
   int a_cols_tenant;  // TMEM columns of one tenant's sign tile per unit: 32 (16-bit signs) or 16 (e4m3 signs)
@@ -210,7 +213,7 @@ template <bool TRACE>
 __device__ __forceinline__ void trace_mark(const UmmaArgs& a, int it, int slot) {
   if (TRACE && a.trace != nullptr && blockIdx.x == 0 && it < 64) a.trace[it * 16 + slot] = clock64();
 }
-__device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return c * a.units_per_cta + min(c, a.units_rem); }
+__device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return a.unit_quantum * (c * a.units_per_cta + min(c, a.units_rem)); }
 
 // Hardware named barriers (ids 0..15): far cheaper than mbarriers.  id 0 = __syncthreads, 1 = epilogue, 2 = release of the
 // unpack group, kBarAFull0 + b = "A buffer b is written" (unpack warps + permute warp arrive, the MMA warp syncs).
@@ -242,6 +245,17 @@ struct Ring {
   uint32_t phase = 0;
   __device__ __forceinline__ void advance(int n) {
     if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+};
+
+// Position in the unit space: K block kb of row chunk mc of N tile nt (tile id = nt * m_chunks + mc).
+struct UnitCursor {
+  int nt, mc, kb;
+  __device__ __forceinline__ void next(int kblocks, int m_chunks) {
+    if (++kb == kblocks) {
+      kb = 0;
+      if (++mc == m_chunks) { mc = 0; ++nt; }
+    }
   }
 };
 
@@ -313,6 +327,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   }
   const int u_begin = cta_unit_begin(a, cta), u_end = cta_unit_begin(a, cta + 1);
   const int tile0 = u_begin / a.kblocks, kb0 = u_begin - tile0 * a.kblocks;  // the only division by kblocks
+  const int nt0 = tile0 / a.m_chunks, mc0 = tile0 - nt0 * a.m_chunks;       // n tile and row chunk of the first tile
   // The activation permutation is done by the dedicated warp alone when it is small (decode), otherwise shared with
   // the unpack warps.
   const int xjobs = DELTA8 ? a.rows * 16 : a.rows * 8;
@@ -418,28 +433,28 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // ===================================================== TMA producer
     if (lane == 0) {
       Ring st;
-      int tile = tile0, kb = kb0;
+      UnitCursor cur{nt0, mc0, kb0};
       // Prologue under PDL: the weight and sign tiles of the first `stages` units are static data and are requested
       // right away; the activation tiles are produced by the previous kernel of the stream, so those loads are issued
       // only after griddepcontrol.wait.  Each stage's barrier expects all three loads.
       {
         const int npre = min(a.stages, u_end - u_begin);
-        int t2 = tile, k2 = kb;
+        UnitCursor c2 = cur;
         for (int i = 0; i < npre; ++i) {
           uint8_t* sp = smem + (size_t)i * a.stage_bytes;
           mbar_arrive_expect_tx(&bar_full[i], a.tx_bytes);
-          const int sg = (t2 >= a.seg_tile0[1]) + (t2 >= a.seg_tile0[2]);
-          const int lt = t2 - a.seg_tile0[sg];
-          if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[i], k2 * kBlockK, lt * kTileN, kEvictFirst);
-          tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[i], lt * kTileN, k2 * (kBlockK / 32), 0, kEvictFirst);
-          if (++k2 == a.kblocks) { k2 = 0; ++t2; }
+          const int sg = (c2.nt >= a.seg_tile0[1]) + (c2.nt >= a.seg_tile0[2]);
+          const int lt = c2.nt - a.seg_tile0[sg];
+          if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[i], c2.kb * kBlockK, lt * kTileN, kEvictFirst);
+          tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[i], lt * kTileN, c2.kb * (kBlockK / 32), 0, kEvictFirst);
+          c2.next(a.kblocks, a.m_chunks);
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int i = 0; i < npre; ++i) {
           trace_mark<TRACE>(a, i, 8);
-          tma_load_2d(smem + (size_t)i * a.stage_bytes + a.off_x, &tmap_x, &bar_full[i], kb * kBlockK, 0, kEvictLast);
+          tma_load_2d(smem + (size_t)i * a.stage_bytes + a.off_x, &tmap_x, &bar_full[i], cur.kb * kBlockK, cur.mc * a.m, kEvictLast);
           st.advance(a.stages);
-          if (++kb == a.kblocks) { kb = 0; ++tile; }
+          cur.next(a.kblocks, a.m_chunks);
         }
       }
 #pragma unroll 1
@@ -448,13 +463,15 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         trace_mark<TRACE>(a, u - u_begin, 8);
         uint8_t* sp = smem + (size_t)st.idx * a.stage_bytes;
         mbar_arrive_expect_tx(&bar_full[st.idx], a.tx_bytes);
-        const int sg = (tile >= a.seg_tile0[1]) + (tile >= a.seg_tile0[2]);
-        const int lt = tile - a.seg_tile0[sg];
-        if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[st.idx], kb * kBlockK, lt * kTileN, kEvictFirst);
-        tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[st.idx], lt * kTileN, kb * (kBlockK / 32), 0, kEvictFirst);
-        tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], kb * kBlockK, 0, kEvictLast);
+        const int sg = (cur.nt >= a.seg_tile0[1]) + (cur.nt >= a.seg_tile0[2]);
+        const int lt = cur.nt - a.seg_tile0[sg];
+        // with row chunks the same W / sign tile is re-read for every chunk of the tile: keep it in L2 (evict-last)
+        const uint64_t whint = a.m_chunks > 1 ? kEvictLast : kEvictFirst;
+        if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[st.idx], cur.kb * kBlockK, lt * kTileN, whint);
+        tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[st.idx], lt * kTileN, cur.kb * (kBlockK / 32), 0, whint);
+        tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], cur.kb * kBlockK, cur.mc * a.m, kEvictLast);
         st.advance(a.stages);
-        if (++kb == a.kblocks) { kb = 0; ++tile; }
+        cur.next(a.kblocks, a.m_chunks);
       }
     }
   } else if (warp == kWarpMma) {
@@ -533,10 +550,12 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
       wait_released(&s_released, u - u_begin);
-      if (!xperm_shared && !(a.dbg_flags & 1)) {
+      if (!(a.dbg_flags & 1)) {
         const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
         uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
-        for (int job = (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += kXpermWarps * 32) xperm_job(xsrc, xp, job);
+        // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
+        const int j0 = xperm_shared ? kUnpackWarps * 32 : 0, jstride = xperm_shared ? (kUnpackWarps + kXpermWarps) * 32 : kXpermWarps * 32;
+        for (int job = j0 + (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += jstride) xperm_job(xsrc, xp, job);
         fence_proxy_async();
       }
       if (warp == kWarpXperm0 && lane == 0) trace_mark<TRACE>(a, u - u_begin, 10);
@@ -571,7 +590,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     uint32_t sign_mask = DELTA8 ? 0x80808080u : 0x80008000u;
     asm volatile("" : "+r"(sign_mask));  // keep the mask in a register so mask + constant fit one LOP3
     Ring st, ab;
-    int tile = tile0, kb = kb0, seg_kb0 = kb0;
+    int tile = tile0, nt = nt0, mc = mc0, kb = kb0, seg_kb0 = kb0;  // tile id = nt * m_chunks + mc
     bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
     uint32_t dphase = 0;
     // Sign words of one unit -> +-1.0 operand registers -> TMEM A buffer `abi` (this warp's tenants, this thread's row).
@@ -638,7 +657,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const uint8_t* sp = smem + (size_t)st_i.idx * a.stage_bytes;
           if (xperm_shared) {  // large row counts: the unpack warps share the activation permutation
             uint8_t* xp = smem + a.off_xp + (size_t)ab_i.idx * a.xp_buf_bytes;
-            for (int job = ut; job < xjobs; job += kUnpackWarps * 32) xperm_job(sp + a.off_x, xp, job);
+            for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) xperm_job(sp + a.off_x, xp, job);
           }
           unpack_unit(sp, ab_i.idx);
           st_i.advance(a.stages);
@@ -662,7 +681,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       if ((a.dbg_flags & 1) && seg_last) {
         mbar_wait(&bar_dfull, dphase);
         dphase ^= 1u;
-        if (++kb == a.kblocks) { kb = 0; ++tile; }
+        if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
         seg_kb0 = kb;
         seg_is_first = false;
         continue;
@@ -676,8 +695,11 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         tc_fence_after();
         const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
         // which matrix of a grouped launch this tile belongs to
-        const int sg = (tile >= a.seg_tile0[1]) + (tile >= a.seg_tile0[2]);
-        const int ltile = tile - a.seg_tile0[sg];
+        const int sg = (nt >= a.seg_tile0[1]) + (nt >= a.seg_tile0[2]);
+        const int ltile = nt - a.seg_tile0[sg];
+        // row chunk of a prefill-size launch: rows [mc*m, mc*m + m_here) of the tenant
+        const int r_off = mc * a.m;
+        const int m_here = min(a.m, a.m_total - r_off);
         const int64_t seg_n = a.n_seg[sg];
         T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
         const void* seg_coeff = a.coeff_seg[sg];
@@ -720,23 +742,27 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
           for (int c8 = 0; c8 < a.mp / 8; ++c8) {
             if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
-            if (c8 * 8 >= a.m) continue;
+            if (c8 * 8 >= m_here) continue;
             float dv[8], bv[8];
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
+            if (HAS_BASE && a.T == 1) {
+              tmem_ld8(tmem_base + lane_addr + col_dbase + c8 * 8, bv);  // one tenant: base columns line up with the chunk
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              bv[i] = 0.f;
-              if (HAS_BASE && c8 * 8 + i < a.m) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
+              for (int i = 0; i < 8; ++i) {
+                bv[i] = 0.f;
+                if (HAS_BASE && c8 * 8 + i < m_here) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
+              }
             }
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int ii = c8 * 8 + i;
-              if (ii >= a.m) continue;
+              if (ii >= m_here) continue;
               const int r = t * a.m + ii;
               const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
               if (full_k) {
-                if (n < seg_n) y[(int64_t)r * seg_n + n] = F16<T16>::from_f32(v);
+                if (n < seg_n) y[(int64_t)(r_off + r) * seg_n + n] = F16<T16>::from_f32(v);
               } else {
                 part[(size_t)r * kTileN + row] = v;
               }
@@ -763,7 +789,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
             // Deterministic reduction with memory-level parallelism: work item = (output row r, 4 consecutive weight
             // rows); the slots of all contributors are fetched with independent 16-byte L2 loads, 8 in flight per
             // thread, and added in K order.  (A serial loop over ~18 contributors cost a 10 us tail per launch.)
-            const int items = a.rows * (kTileN / 4);
+            const int items = (a.m_chunks > 1 ? m_here : a.rows) * (kTileN / 4);
             for (int item = ut; item < items; item += kUnpackWarps * 32) {
               const int r = item / (kTileN / 4), q4 = item - r * (kTileN / 4);
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -782,7 +808,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
                 for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
               }
               const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
-              T16* dst = y + (int64_t)r * seg_n + n4;
+              T16* dst = y + (int64_t)(r_off + r) * seg_n + n4;
               if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte aligned for these 4 elements
                 const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
                 *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
@@ -794,7 +820,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         seg_is_first = false;
         if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 3] = clock64();
       }
-      if (++kb == a.kblocks) { kb = 0; ++tile; }
+      if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
       if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
     }
   }
@@ -973,6 +999,14 @@ size_t umma_workspace_bytes(int64_t rows, int64_t N) {
 
 static int launch_one(const FwdProblem& p) {
   int64_t T = p.T, m = p.m;
+  // Prefill-size launches of ONE tenant are processed in row chunks of 128 inside the launch: tile = (N tile, row chunk)
+  const int64_t m_total = m;
+  int64_t m_chunks = 1;
+  if (T == 1 && m > kMaxRows) {
+    if (p.nseg > 1) return fail(BD_ERR_UNSUPPORTED, "grouped launch: more than %d rows", kMaxRows);
+    m_chunks = (m + kMaxRows - 1) / kMaxRows;
+    m = kMaxRows;
+  }
   const bool has_base = p.w != nullptr;
   const int nseg = p.nseg < 1 ? 1 : p.nseg;
   if (nseg > kMaxSeg) return fail(BD_ERR_INVALID, "tcgen05 kernel: at most %d matrices per grouped launch", kMaxSeg);
@@ -1014,11 +1048,21 @@ static int launch_one(const FwdProblem& p) {
     tiles += (int)((Ns[sg] + kTileN - 1) / kTileN);
   }
   if (tiles > (int)(kWsCounterBytes / sizeof(unsigned))) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: too many N tiles");
-  a.n_tiles = tiles;
+  a.m_chunks = (int)m_chunks;
+  a.m_total = (int)m_total;
+  const int64_t total_tiles = (int64_t)tiles * m_chunks;
+  if (total_tiles * a.kblocks > 0x7fffffff) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: problem too large for one launch");
+  a.n_tiles = (int)total_tiles;
   a.total_units = a.n_tiles * a.kblocks;
   const int grid = a.total_units < di.sms ? a.total_units : di.sms;
-  a.units_per_cta = a.total_units / grid;
-  a.units_rem = a.total_units % grid;
+  // Many tiles per CTA: hand out whole tiles (no split-K fix-up, whose partials grow with the row count); otherwise
+  // stream-K over single units so that every SM streams the same number of bytes.
+  const bool whole_tiles = total_tiles >= 4 * (int64_t)grid;
+  a.unit_quantum = whole_tiles ? a.kblocks : 1;
+  const int sched_units = whole_tiles ? a.n_tiles : a.total_units;
+  a.units_per_cta = sched_units / grid;
+  a.units_rem = sched_units % grid;
+  if (!whole_tiles && a.n_tiles > (int)(kWsCounterBytes / sizeof(unsigned))) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: too many tiles for the split-K counters");
   a.n_abuf = plan.n_abuf;
   a.a_cols_tenant = plan.a_cols_tenant;
   a.stages = plan.stages; a.stage_bytes = plan.stage_bytes; a.off_masks = plan.off_masks; a.off_x = plan.off_x;
@@ -1046,7 +1090,7 @@ static int launch_one(const FwdProblem& p) {
     if ((rc = encode_map(&maps.m[sg], CU_TENSOR_MAP_DATA_TYPE_INT32, 3, ms[sg], dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "masks"))) return rc;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)rows}, str[1] = {(cuuint64_t)p.K * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)(T * m_total)}, str[1] = {(cuuint64_t)p.K * 2};
     cuuint32_t box[2] = {kBlockK, (cuuint32_t)plan.ntb};
     if ((rc = encode_map(&maps.x, dt16, 2, p.x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
   }
@@ -1109,6 +1153,7 @@ int launch_fwd_umma(const FwdProblem& p0) {
     }
     return BD_OK;
   }
+  if (p.T == 1 && p.m > kMaxRows && p.nseg <= 1 && p.m <= (1 << 20)) return launch_one(p);  // row chunks inside the launch
   if (p.m > kMaxRows) {
     for (int64_t r0 = 0; r0 < p.m; r0 += kMaxRows) {
       FwdProblem s = p;

@@ -12,6 +12,7 @@ cases = [  # T, m, K, N, has_base
     (1, 1, 64, 128, True), (1, 1, 64, 128, False), (1, 1, 128, 128, True), (1, 3, 256, 256, True), (2, 1, 128, 128, True),
     (6, 1, 4096, 4096, True), (6, 1, 4096, 1024, True), (6, 1, 14336, 4096, True), (6, 1, 4096, 14336, True),
     (6, 2, 512, 384, True), (1, 16, 4096, 4096, True), (1, 128, 1024, 512, True), (4, 16, 256, 256, False), (1, 5, 96, 200, True),
+    (1, 300, 1024, 512, True), (1, 2048, 4096, 4096, True), (1, 1000, 512, 1280, False), (2, 200, 256, 256, True),
 ]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
