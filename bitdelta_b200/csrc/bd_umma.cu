@@ -304,7 +304,10 @@ __host__ __device__ constexpr uint32_t make_idesc8(int n) {
   return (1u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
 }
 
-template <typename T16, bool HAS_BASE, bool DELTA8, bool TRACE>
+// NATK (one tenant on the 16-bit path): the sign tile is unpacked in NATURAL K order (register i = elements 2i, 2i+1), so the
+// delta MMAs read the very same TMA-loaded activation tile as the base MMAs and no K-permuted copy is built at all.  It
+// costs 4 ALU ops per register instead of 2, which is nothing for a single tenant -- and prefill is tensor-bound.
+template <typename T16, bool HAS_BASE, bool DELTA8, bool NATK, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   const CUtensorMap& tmap_x = maps.x;
@@ -523,7 +526,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
               }
             }
           } else {
-            uint32_t d = d_delta, at = a_tmem0 + ks * 8, bl = xp_lo + ks * 2;
+            uint32_t d = d_delta, at = a_tmem0 + ks * 8, bl = (NATK ? x_lo : xp_lo) + ks * 2;
 #pragma unroll 2
             for (int t = 0; t < a.T; ++t) {
               mma_ts_lo(d, at, bl, idesc_delta, acc);
@@ -550,7 +553,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
       wait_released(&s_released, u - u_begin);
-      if (!(a.dbg_flags & 1)) {
+      if (!NATK && !(a.dbg_flags & 1)) {
         const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
         uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
         // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
@@ -625,7 +628,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
               uint32_t r[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const uint32_t sh = w << (15 - i);               // bit i -> 15, bit i+16 -> 31
+                uint32_t sh;
+                if constexpr (NATK) {
+                  // natural K order: bits 2i, 2i+1 -> 15, 31:  ((w >> 2i) & 3) * 0x40008000 has them at 15/30 and 16/31
+                  sh = ((w >> (2 * i)) & 3u) * 0x40008000u;
+                } else {
+                  sh = w << (15 - i);                            // bit i -> 15, bit i+16 -> 31
+                }
                 // r = (~sh & 0x80008000) | one : sign = ~bit, bit 1 -> +1.0, bit 0 -> -1.0.  One LOP3 (LUT 0xAE).
                 asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[i]) : "r"(sh), "r"(sign_mask), "r"(kOne));
               }
@@ -655,7 +664,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       if (!(a.dbg_flags & 1)) {
         for (int i = 0; i < g; ++i) {
           const uint8_t* sp = smem + (size_t)st_i.idx * a.stage_bytes;
-          if (xperm_shared) {  // large row counts: the unpack warps share the activation permutation
+          if (!NATK && xperm_shared) {  // large row counts: the unpack warps share the activation permutation
             uint8_t* xp = smem + a.off_xp + (size_t)ab_i.idx * a.xp_buf_bytes;
             for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) xperm_job(sp + a.off_x, xp, job);
           }
@@ -665,7 +674,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         }
         if (tr) trace_mark<TRACE>(a, it, 3);
         tc_wait_st();
-        if (xperm_shared) fence_proxy_async();
+        if (!NATK && xperm_shared) fence_proxy_async();
       }
       tc_fence_before();
       if (tr) trace_mark<TRACE>(a, it, 4);
@@ -877,7 +886,7 @@ struct UmmaPlan {
   bool ok = false;
   const char* why = "";
   int mp = 0, ntb = 0, stages = 0, n_abuf = 0, a_cols_tenant = 0;
-  bool d8 = false;
+  bool d8 = false, natk = false;
   uint32_t stage_bytes = 0, off_masks = 0, off_x = 0, off_xp = 0, xp_buf_bytes = 0, smem_bytes = 0, tx_bytes = 0;
 };
 
@@ -899,7 +908,8 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
   if (nbuf < 2) { p.why = "accumulators + sign operand buffers exceed 512 TMEM columns"; return p; }
   if (nbuf > kMaxABuf) nbuf = kMaxABuf;
   // the K-permuted activation tiles (one set per A buffer) live in shared memory: keep them under 48 KiB
-  const int64_t xp_one = d8 ? T * 1024 : T * p.mp * 128;
+  p.natk = !d8 && T == 1;  // one tenant, 16-bit signs: natural K order, no permuted activation copy
+  const int64_t xp_one = p.natk ? 1024 : (d8 ? T * 1024 : T * p.mp * 128);
   while (nbuf > 2 && nbuf * xp_one > 48 * 1024) --nbuf;
   p.n_abuf = (int)nbuf;
   const uint32_t w_bytes = has_base ? kTileN * kBlockK * 2 : 0;
@@ -944,9 +954,9 @@ int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* b
   return BD_OK;
 }
 
-template <typename T16, bool HAS_BASE, bool DELTA8, bool TRACE>
+template <typename T16, bool HAS_BASE, bool DELTA8, bool NATK, bool TRACE>
 int launch_typed(const FwdProblem& p, const UmmaPlan& plan, const UmmaMaps& maps, const UmmaArgs& args, int grid) {
-  auto kern = fwd_umma_kernel<T16, HAS_BASE, DELTA8, TRACE>;
+  auto kern = fwd_umma_kernel<T16, HAS_BASE, DELTA8, NATK, TRACE>;
   static std::once_flag once;  // one per template instantiation
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); });
@@ -1096,15 +1106,21 @@ static int launch_one(const FwdProblem& p) {
   }
   if (p.dtype == BD_BF16) {
     if (plan.d8) {
-      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, true>(p, plan, maps, a, grid);  // instrumented build
-      return has_base ? launch_typed<__nv_bfloat16, true, true, false>(p, plan, maps, a, grid)
-                      : launch_typed<__nv_bfloat16, false, true, false>(p, plan, maps, a, grid);
+      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, false, true>(p, plan, maps, a, grid);  // instrumented build
+      return has_base ? launch_typed<__nv_bfloat16, true, true, false, false>(p, plan, maps, a, grid)
+                      : launch_typed<__nv_bfloat16, false, true, false, false>(p, plan, maps, a, grid);
     }
-    return has_base ? launch_typed<__nv_bfloat16, true, false, false>(p, plan, maps, a, grid)
-                    : launch_typed<__nv_bfloat16, false, false, false>(p, plan, maps, a, grid);
+    if (plan.natk)
+      return has_base ? launch_typed<__nv_bfloat16, true, false, true, false>(p, plan, maps, a, grid)
+                      : launch_typed<__nv_bfloat16, false, false, true, false>(p, plan, maps, a, grid);
+    return has_base ? launch_typed<__nv_bfloat16, true, false, false, false>(p, plan, maps, a, grid)
+                    : launch_typed<__nv_bfloat16, false, false, false, false>(p, plan, maps, a, grid);
   }
-  return has_base ? launch_typed<__half, true, false, false>(p, plan, maps, a, grid)
-                  : launch_typed<__half, false, false, false>(p, plan, maps, a, grid);
+  if (plan.natk)
+    return has_base ? launch_typed<__half, true, false, true, false>(p, plan, maps, a, grid)
+                    : launch_typed<__half, false, false, true, false>(p, plan, maps, a, grid);
+  return has_base ? launch_typed<__half, true, false, false, false>(p, plan, maps, a, grid)
+                  : launch_typed<__half, false, false, false, false>(p, plan, maps, a, grid);
 }
 
 void umma_set_trace(long long* buf) { g_trace_buf = buf; }
