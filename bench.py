@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -281,6 +281,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         barrier()
         ms_e2e_total = f0.elapsed_time(f1)
 
+    # ---- the other half of the headline metric: W1A16 GEMM throughput at prefill size (one BinaryDiff linear, 4096 tokens) ----
+    gemm = None
+    if rank == 0 and not args.no_gemm:
+        with torch.cuda.stream(stream):
+            Mg, Ng, Kg = 4096, 4096, 4096
+            lin = mods[0]["q_proj"]
+            xg = torch.randn(1, Mg, Kg, generator=gen, device=dev).bfloat16()
+            one = bd.DiffCompressModule(lin.module, lin.mask[:1].contiguous(), lin.coeff[:1].contiguous())
+            for _ in range(3):
+                one(xg)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(10):
+                one(xg)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            us = g0.elapsed_time(g1) * 1e3 / 10
+            tf = 4.0 * Mg * Ng * Kg / us / 1e6
+            gemm = {"shape": f"M={Mg} tokens x N={Ng} x K={Kg}, 1 delta (BinaryDiff prefill)", "us": us, "tflops": tf,
+                    "flops_counted": "4*M*N*K (base product + sign product, as the reference's notebook counts them)"}
+
     times = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -328,6 +349,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if gemm is not None:
+            gemm["frac_of_measured_bf16_peak"] = gemm["tflops"] / tf_peak
+            gemm["peak_tflops"] = tf_peak
+            line["w1a16_gemm"] = gemm
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -337,11 +362,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers (the result is labelled DEBUG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gemm", action="store_true", help="skip the prefill-size W1A16 GEMM measurement")
     ap.add_argument("--no-group", action="store_true", help="one launch per linear (no q/k/v and gate/up grouping)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

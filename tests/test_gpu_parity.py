@@ -228,7 +228,7 @@ def test_config1_single_4096_linear(kernel, M, dtype):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("N,K,rows", [(50, 32, 3), (64, 64, 1), (200, 96, 9), (1024, 4096, 6), (72, 2080, 17), (132, 160, 128), (4100, 4128, 2)])
+@pytest.mark.parametrize("N,K,rows", [(50, 32, 3), (64, 64, 1), (200, 96, 9), (1024, 4096, 6), (72, 2080, 17), (132, 160, 128), (4100, 4128, 2), (640, 1024, 700), (4096, 4096, 1500)])
 def test_forward_ragged_shapes(kernel, N, K, rows):
     torch.manual_seed(N + K + rows)
     base = (torch.randn(N, K) * 0.05).bfloat16()
@@ -309,7 +309,7 @@ def test_dataparallel_reference_vectors(golden):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("N,K,m,T", [(1024, 4096, 1, 6), (4096, 14336, 1, 6), (4096, 4096, 3, 6), (1024, 8192, 1, 8), (512, 1024, 20, 3)])
+@pytest.mark.parametrize("N,K,m,T", [(1024, 4096, 1, 6), (4096, 14336, 1, 6), (4096, 4096, 3, 6), (1024, 8192, 1, 8), (512, 1024, 20, 3), (384, 512, 150, 2)])
 def test_mistral_shapes_six_tenants(kernel, N, K, m, T):
     # BASELINE config 3 shapes (k_proj, down_proj, q_proj), T = 6 tenants, decode rows; config 5's 8 tenants (two
     # launches of the tcgen05 kernel) and a multi-tenant case with more than 16 rows per tenant (one launch per tenant)
