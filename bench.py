@@ -302,6 +302,47 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             gemm = {"shape": f"M={Mg} tokens x N={Ng} x K={Kg}, 1 delta (BinaryDiff prefill)", "us": us, "tflops": tf,
                     "flops_counted": "4*M*N*K (base product + sign product, as the reference's notebook counts them)"}
 
+    # ---- next row: the per-tenant dense leaves of the same decode step, each ONE native launch over the tenants ----
+    leaves = None
+    if rank == 0 and not args.no_gemm:
+        with torch.cuda.stream(stream):
+            vocab = (32000, 32000, 32002, 32002, 32002, 32002)  # the six demo tenants
+            heads = [(torch.randn(v, 4096, generator=gen, device=dev) * 0.02).bfloat16() for v in vocab]
+            head = bd.DataParallelModule(torch.nn.Linear(4096, vocab[0], bias=False, device=dev, dtype=torch.bfloat16), heads)
+            class MistralRMSNorm(torch.nn.Module):  # the HF module's attributes; its forward is the native kernel's arithmetic
+                def __init__(self):
+                    super().__init__()
+                    self.weight = torch.nn.Parameter(torch.ones(4096, device=dev, dtype=torch.bfloat16))
+                    self.variance_epsilon = 1e-5
+
+            norm_mod = MistralRMSNorm()
+            norm = bd.DataParallelModule(norm_mod, [torch.ones(4096, device=dev, dtype=torch.bfloat16) for _ in vocab])
+            emb = bd.DataParallelModule(torch.nn.Embedding(vocab[0], 4096, device=dev, dtype=torch.bfloat16), heads)
+            xh = torch.randn(TENANTS, 1, 4096, generator=gen, device=dev).bfloat16()
+            ids = torch.randint(0, 32000, (TENANTS, 1), device=dev)
+
+            def timed(fn, n):
+                for _ in range(3):
+                    fn()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(stream)
+                for _ in range(n):
+                    fn()
+                t1.record(stream)
+                torch.cuda.synchronize(dev)
+                return t0.elapsed_time(t1) * 1e3 / n
+
+            us_head = timed(lambda: head(xh), 20)
+            us_norm = timed(lambda: norm(xh), 50)
+            us_emb = timed(lambda: emb(ids), 50)
+            head_bytes = sum(v * 4096 * 2 for v in vocab) + TENANTS * 4096 * 2 + TENANTS * max(vocab) * 2
+            leaves = {"lm_head": {"us": us_head, "algorithmic_bytes": head_bytes, "gbps": head_bytes / us_head / 1e3,
+                                  "vocab": list(vocab), "note": "weights (1.57 GB) exceed L2: every launch streams from HBM"},
+                      "rmsnorm_us": us_norm, "embed_us": us_emb,
+                      "step_extra_ms": (us_head + 65 * us_norm + us_emb) / 1e3,
+                      "note": "not part of `value`: 1 lm_head + 65 RMSNorm + 1 embedding launches per decode step"}
+            del heads, head, emb
+
     times = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -353,6 +394,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             gemm["frac_of_measured_bf16_peak"] = gemm["tflops"] / tf_peak
             gemm["peak_tflops"] = tf_peak
             line["w1a16_gemm"] = gemm
+        if leaves is not None:
+            leaves["lm_head"]["frac"] = leaves["lm_head"]["gbps"] / hbm_peak
+            line["tenant_leaves"] = leaves
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

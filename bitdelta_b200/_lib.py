@@ -24,6 +24,7 @@ EXPORTS = [
     "bd_pack", "bd_unpack", "bd_pack_host", "bd_unpack_host",
     "bd_compress", "bd_fold",
     "bd_binary_bmm", "bd_binarydiff_fwd_batched", "bd_binarydiff_fwd_grouped",
+    "bd_tenant_linear", "bd_tenant_rmsnorm", "bd_tenant_embed",
     "bd_workspace_bytes", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags",
 ]
 
@@ -53,6 +54,9 @@ def _load() -> ctypes.CDLL:
     lib.bd_binary_bmm.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i64, vp, sz, i32, vp]
     lib.bd_binarydiff_fwd_batched.argtypes = [vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, i64, i64, vp, sz, i32, vp]
     lib.bd_binarydiff_fwd_grouped.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i64, i64, i64, vp, sz, i32, vp]
+    lib.bd_tenant_linear.argtypes = [vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp]
+    lib.bd_tenant_rmsnorm.argtypes = [vp, vp, vp, i32, i64, i64, i64, c.c_float, vp]
+    lib.bd_tenant_embed.argtypes = [vp, vp, vp, vp, i32, i64, i64, i64, vp]
     lib.bd_workspace_bytes.argtypes = [i64, i64]
     lib.bd_workspace_bytes.restype = sz
     lib.bd_select_kernel.argtypes = [i32, i64, i64, i64, i64, i32]

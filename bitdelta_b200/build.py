@@ -12,7 +12,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libbitdelta_b200.so")
-SOURCES = ["bd_api.cu", "bd_codec.cu", "bd_simt.cu", "bd_umma.cu"]
+SOURCES = ["bd_api.cu", "bd_codec.cu", "bd_simt.cu", "bd_umma.cu", "bd_tenant.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",

@@ -12,19 +12,71 @@ and all tenants' 1-bit deltas, with the per-tenant coefficient applied in the fp
 """
 from __future__ import annotations
 
+import ctypes
 import gc
 
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .diff import _fused_forward, _fused_forward_grouped
+
+
+TENANT_LINEAR_MAX_ROWS = 4  # BD_TENANT_LINEAR_MAX_ROWS: decode-size launches; larger m is a plain library GEMM per tenant
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _native_leaf_ok(x, weights):
+    w0 = weights[0]
+    return (x.is_cuda and w0.dtype in (torch.bfloat16, torch.float16)
+            and all(w.device == x.device and w.dtype == w0.dtype and w.is_contiguous() for w in weights))
+
+
+def tenant_linear(x, weights, bias=None):
+    """One launch of ``bd_tenant_linear``: ``y[t] = x[t] @ weights[t].T`` right-padded with ``finfo.min`` to the widest
+    tenant (reference :72-79).  x: [T, m, K] with m <= 4."""
+    T, m, K = x.shape
+    sizes = [int(w.shape[0]) for w in weights]
+    ldy = max(sizes)
+    y = torch.empty((T, m, ldy), device=x.device, dtype=x.dtype)
+    n_out = (ctypes.c_int64 * T)(*sizes)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.bd_tenant_linear(x.data_ptr(), _ptr_array(weights), n_out, bias.data_ptr() if bias is not None else None,
+                                             y.data_ptr(), _lib.dtype_code(x.dtype), T, m, K, ldy, _lib.stream_ptr(x.device)))
+    return y
+
+
+def tenant_rmsnorm(x, weights, eps):
+    """One launch of ``bd_tenant_rmsnorm`` (HF Llama/Mistral RMSNorm arithmetic with tenant t's weight on row t)."""
+    T, H = x.shape[0], x.shape[-1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib.bd_tenant_rmsnorm(x.data_ptr(), _ptr_array(weights), y.data_ptr(), _lib.dtype_code(x.dtype), T,
+                                              x.numel() // (T * H), H, float(eps), _lib.stream_ptr(x.device)))
+    return y
+
+
+def tenant_embed(ids, weights):
+    """One launch of ``bd_tenant_embed``: ``y[t, i] = weights[t][ids[t, i]]``."""
+    T, H = ids.shape[0], int(weights[0].shape[1])
+    y = torch.empty(tuple(ids.shape) + (H,), device=ids.device, dtype=weights[0].dtype)
+    n_rows = (ctypes.c_int64 * T)(*[int(w.shape[0]) for w in weights])
+    with torch.cuda.device(ids.device):
+        _lib.check(_lib.lib.bd_tenant_embed(ids.data_ptr(), _ptr_array(weights), n_rows, y.data_ptr(), _lib.dtype_code(y.dtype), T,
+                                            ids.numel() // T, H, _lib.stream_ptr(ids.device)))
+    return y
 
 
 class DataParallelModule(nn.Module):
     """Per-tenant full-precision leaf (embed_tokens, RMSNorm, lm_head): row i uses ``weight_list[i]`` (:62-79).
 
     Outputs of different width (ragged vocabularies) are right-padded with ``finfo(dtype).min`` exactly like the
-    reference's nested-tensor padding (:78-79).
+    reference's nested-tensor padding (:78-79).  On a CUDA device the three leaf kinds the demo wraps run as ONE native
+    launch over all tenants (``bd_tenant_linear`` / ``bd_tenant_rmsnorm`` / ``bd_tenant_embed``); any other module type
+    keeps the reference's generic loop (swap ``weight.data``, call the module on row i).
     """
 
     def __init__(self, module, weight_list):
@@ -33,7 +85,37 @@ class DataParallelModule(nn.Module):
         self.weight_list = weight_list
         self.original_weight = module.weight.data
 
+    def _native(self, x):
+        mod, ws = self.module, self.weight_list
+        T = len(ws)
+        if not x.is_cuda or x.shape[0] != T or x.dim() < 2:
+            return None
+        if isinstance(mod, nn.Embedding):
+            if (x.dtype == torch.int64 and mod.max_norm is None and _native_leaf_ok(x, ws)
+                    and len({int(w.shape[1]) for w in ws}) == 1):
+                return tenant_embed(x.contiguous(), ws)
+            return None
+        if not (x.dtype == ws[0].dtype and _native_leaf_ok(x, ws)):
+            return None
+        if isinstance(mod, nn.Linear):
+            K = x.shape[-1]
+            m = x.numel() // (T * K)
+            sizes = {int(w.shape[0]) for w in ws}
+            bias = mod.bias
+            if (1 <= m <= TENANT_LINEAR_MAX_ROWS and K % 8 == 0 and all(w.shape[1] == K and w.data_ptr() % 16 == 0 for w in ws)
+                    and (bias is None or (len(sizes) == 1 and bias.dtype == x.dtype and bias.is_cuda))):
+                y = tenant_linear(x.contiguous().view(T, m, K), ws, bias)
+                return y.view(tuple(x.shape[:-1]) + (y.shape[-1],))
+            return None
+        if hasattr(mod, "variance_epsilon") and ws[0].dim() == 1 and type(mod).__name__.endswith(("RMSNorm", "LayerNorm")) \
+                and not hasattr(mod, "bias") and all(w.shape[0] == x.shape[-1] for w in ws):
+            return tenant_rmsnorm(x.contiguous(), ws, mod.variance_epsilon)
+        return None
+
     def forward(self, hidden_states):
+        y = self._native(hidden_states)
+        if y is not None:
+            return y
         outputs = []
         for i in range(len(self.weight_list)):
             self.module.weight.data = self.weight_list[i]

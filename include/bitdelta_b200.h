@@ -113,6 +113,29 @@ BD_API int bd_binarydiff_fwd_grouped(const void* x, int nseg, const void* const*
                               int coeff_dtype, void* const* y, const int64_t* N, const int64_t* mask_tenant_stride, int dtype,
                               int64_t T, int64_t m, int64_t K, void* workspace, size_t workspace_bytes, int kernel, void* stream);
 
+/* ---- a8: per-tenant dense leaves, DataParallelModule.forward (demo/demo_backend.py:69-79) --------------------
+ * Row t of the batch goes through tenant t's own full-precision weight; one launch covers all tenants instead of
+ * the reference's host loop (weight.data swap + module call per tenant, :72-74) and nested-tensor padding (:77-79).
+ * `w` is a HOST array of T device pointers (tenant weights are separate tensors in the checkpoints); it is copied
+ * into the kernel parameters, so the calls are asynchronous and graph-capturable.
+ *
+ * bd_tenant_linear  (lm_head):  y[t,i,v] = x[t,i,:] . w[t][v,:]  for v < n_out[t], fp32 accumulate, one rounding;
+ *   columns n_out[t]..ldy-1 are filled with the lowest finite value of `dtype` (torch.finfo(dtype).min, :78).
+ *   x: [T,m,K], w[t]: [n_out[t],K] row-major, y: [T,m,ldy]; m <= BD_TENANT_LINEAR_MAX_ROWS (decode; larger m is a
+ *   plain per-tenant library GEMM and stays with the caller), K % 8 == 0, 16-byte aligned pointers.  `bias` (may be
+ *   NULL) is the wrapped module's shared bias [ldy]; it requires equal widths.
+ * bd_tenant_rmsnorm (HF Llama/Mistral RMSNorm, the class the reference's model instantiates):
+ *   y[t,i,:] = w[t] * round(x[t,i,:] * rsqrt(mean(x[t,i,:]^2) + eps)), statistics in fp32, both roundings to `dtype`.
+ * bd_tenant_embed   (embed_tokens): y[t,i,:] = w[t][ids[t,i], :]; ids int64 [T,m] on the device, n_rows[t] table rows.
+ */
+#define BD_TENANT_LINEAR_MAX_ROWS 4
+BD_API int bd_tenant_linear(const void* x, const void* const* w, const int64_t* n_out, const void* bias, void* y, int dtype,
+                     int64_t T, int64_t m, int64_t K, int64_t ldy, void* stream);
+BD_API int bd_tenant_rmsnorm(const void* x, const void* const* w, void* y, int dtype, int64_t T, int64_t m, int64_t H, float eps,
+                      void* stream);
+BD_API int bd_tenant_embed(const int64_t* ids, const void* const* w, const int64_t* n_rows, void* y, int dtype, int64_t T, int64_t m,
+                    int64_t H, void* stream);
+
 /* Upper bound of the workspace any forward of at most `max_rows` = T*m rows and `max_n` outputs needs on the
  * current device. */
 BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n);

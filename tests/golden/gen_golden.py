@@ -241,10 +241,50 @@ def gen_diff_pt():
     print("diff.pt keys:", len(keys), keys[:4], "...")
 
 
+# ---------------------------------------------------------------- 7. per-tenant dense leaves (DataParallelModule, demo_backend.py:62-79)
+def gen_tenant_leaves():
+    """The reference's DataParallelModule around the three leaf kinds it wraps in the demo: lm_head (ragged vocab),
+    embed_tokens and the HF RMSNorm (transformers' LlamaRMSNorm, the class the decoder layers instantiate)."""
+    from transformers.models.llama.modeling_llama import LlamaRMSNorm
+
+    ns = load_demo_classes()
+    arrs = {}
+    for tag, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        torch.manual_seed(7)
+        T, K = 3, 256
+        vocab = (70, 75, 64)
+        for m in (1, 3):
+            x = torch.randn(T, m, K).to(dt)
+            head = nn.Linear(K, vocab[0], bias=False).to(dt)
+            ws = [(torch.randn(v, K) * 0.05).to(dt) for v in vocab]
+            with torch.no_grad():
+                logits = ns["DataParallelModule"](head, ws)(x)
+            norm = LlamaRMSNorm(K, eps=1e-5).to(dt)
+            nws = [(1.0 + 0.1 * torch.randn(K)).to(dt) for _ in range(T)]
+            with torch.no_grad():
+                normed = ns["DataParallelModule"](norm, nws)(x)
+            emb = nn.Embedding(max(vocab), K).to(dt)
+            ews = [torch.randn(v, K).to(dt) for v in vocab]
+            ids = torch.stack([torch.randint(0, v, (m,)) for v in vocab])
+            with torch.no_grad():
+                e = ns["DataParallelModule"](emb, ews)(ids)
+            pre = f"{tag}_m{m}_"
+            arrs[pre + "x"] = bf16_bits(x)
+            for t in range(T):
+                arrs[pre + f"head_w{t}"] = bf16_bits(ws[t])
+                arrs[pre + f"emb_w{t}"] = bf16_bits(ews[t])
+            arrs[pre + "logits"] = bf16_bits(logits)
+            arrs[pre + "norm_w"] = np.stack([bf16_bits(w) for w in nws])
+            arrs[pre + "normed"] = bf16_bits(normed)
+            arrs[pre + "ids"] = ids.numpy()
+            arrs[pre + "emb_out"] = bf16_bits(e)
+    arrs["eps"] = np.float32(1e-5)
+    save("tenant_leaves.npz", **arrs)
+
+
+GENERATORS = dict(codec=gen_codec, ctor=gen_ctor, triton_interp=gen_triton_interp, forward=gen_forward, demo=gen_demo,
+                  diff_pt=gen_diff_pt, tenant_leaves=gen_tenant_leaves)
+
 if __name__ == "__main__":
-    gen_codec()
-    gen_ctor()
-    gen_triton_interp()
-    gen_forward()
-    gen_demo()
-    gen_diff_pt()
+    for name in (sys.argv[1:] or list(GENERATORS)):
+        GENERATORS[name]()

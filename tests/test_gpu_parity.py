@@ -308,6 +308,110 @@ def test_dataparallel_reference_vectors(golden):
     assert np.array_equal(to_np(out), bf(g["emb_out"]))
 
 
+def t_16(bits: np.ndarray, tag: str) -> torch.Tensor:
+    return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16 if tag == "bf16" else torch.float16)
+
+
+@pytest.mark.parametrize("tag", ["bf16", "fp16"])
+@pytest.mark.parametrize("m", [1, 3])
+def test_tenant_leaves_reference_vectors(golden, tag, m):
+    """DataParallelModule's three native leaf kernels against the reference's own module outputs (gen_tenant_leaves)."""
+    from transformers.models.llama.modeling_llama import LlamaRMSNorm
+
+    from bitdelta_b200 import _lib
+
+    g = golden("tenant_leaves.npz")
+    dt = torch.bfloat16 if tag == "bf16" else torch.float16
+    dec = bf if tag == "bf16" else (lambda b: np.asarray(b).view(np.float16).astype(np.float32))
+    ulp = 2.0**-8 if tag == "bf16" else 2.0**-11
+    pre = f"{tag}_m{m}_"
+    x = t_16(g[pre + "x"], tag).to(DEV)
+    vocab = (70, 75, 64)
+    # lm_head: ragged vocab, finfo.min padding
+    head = torch.nn.Linear(256, vocab[0], bias=False).to(DEV, dt)
+    ws = [t_16(g[pre + f"head_w{t}"], tag).to(DEV) for t in range(3)]
+    n0 = _lib.launch_count()
+    logits = bd.DataParallelModule(head, ws)(x)
+    assert _lib.launch_count() == n0 + 1, "lm_head leaf must be ONE native launch"
+    ref = dec(g[pre + "logits"])
+    got = to_np(logits)
+    assert got.shape == ref.shape == (3, m, 75)
+    for t, v in enumerate(vocab):
+        assert np.array_equal(got[t, :, v:], ref[t, :, v:]) and np.all(ref[t, :, v:] == float(torch.finfo(dt).min))
+        assert np.all(np.abs(got[t, :, :v] - ref[t, :, :v]) <= 2 * ulp * np.abs(ref[t, :, :v]) + 1e-6)
+    # RMSNorm with per-tenant weights (HF LlamaRMSNorm is what the reference's model instantiates)
+    norm = LlamaRMSNorm(256, eps=float(g["eps"])).to(DEV, dt)
+    nws = [t_16(w, tag).to(DEV) for w in g[pre + "norm_w"]]
+    n0 = _lib.launch_count()
+    normed = bd.DataParallelModule(norm, nws)(x)
+    assert _lib.launch_count() == n0 + 1
+    refn = dec(g[pre + "normed"])
+    gotn = to_np(normed)
+    assert np.all(np.abs(gotn - refn) <= 2 * ulp * np.abs(refn) + 1e-6)
+    assert (gotn == refn).mean() > 0.98
+    # embed_tokens
+    emb = torch.nn.Embedding(75, 256).to(DEV, dt)
+    ews = [t_16(g[pre + f"emb_w{t}"], tag).to(DEV) for t in range(3)]
+    n0 = _lib.launch_count()
+    e = bd.DataParallelModule(emb, ews)(torch.from_numpy(g[pre + "ids"]).to(DEV))
+    assert _lib.launch_count() == n0 + 1
+    assert np.array_equal(to_np(e), dec(g[pre + "emb_out"]))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m", [1, 2, 4])
+def test_tenant_linear_lm_head_size(dt, m):
+    """Mistral-7B lm_heads of the six demo tenants (vocab 32000 x2, 32002 x4), decode rows, against the oracle."""
+    torch.manual_seed(3)
+    K, vocab = 4096, (32000, 32000, 32002, 32002, 32002, 32002)
+    x = torch.randn(6, m, K, device=DEV).to(dt)
+    ws = [(torch.randn(v, K, device=DEV) * 0.02).to(dt) for v in vocab]
+    head = torch.nn.Linear(K, vocab[0], bias=False).to(DEV, dt)
+    y = bd.DataParallelModule(head, ws)(x)
+    assert y.shape == (6, m, 32002)
+    assert torch.all(y[:2, :, 32000:] == torch.finfo(dt).min)
+    for t, v in enumerate(vocab):
+        exact = to_np(x[t]).astype(np.float64) @ to_np(ws[t]).astype(np.float64).T
+        assert_close_to_exact(y[t, :, :v], exact, f"lm_head tenant {t}")
+    # same launch under CUDA-graph capture and replay
+    mod = bd.DataParallelModule(head, ws)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        mod(x)
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            yg = mod(x)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(yg, y)
+
+
+def test_tenant_linear_shared_bias_and_many_tenants():
+    """A wrapped Linear with a bias (shared by the tenants, equal widths) and more tenants than one launch group (32)."""
+    torch.manual_seed(4)
+    T, K, N = 37, 264, 45
+    x = torch.randn(T, 1, K, device=DEV).bfloat16()
+    ws = [(torch.randn(N, K, device=DEV) * 0.05).bfloat16() for _ in range(T)]
+    head = torch.nn.Linear(K, N, bias=True).to(DEV, torch.bfloat16)
+    y = bd.DataParallelModule(head, ws)(x)
+    for t in range(T):
+        exact = to_np(x[t]).astype(np.float64) @ to_np(ws[t]).astype(np.float64).T + to_np(head.bias).astype(np.float64)
+        assert_close_to_exact(y[t], exact, f"bias tenant {t}")
+
+
+def test_dataparallel_generic_module_keeps_reference_loop():
+    """A leaf kind without a native kernel (LayerNorm with bias) goes through the reference's per-tenant loop."""
+    torch.manual_seed(5)
+    ln = torch.nn.LayerNorm(64).to(DEV, torch.bfloat16)
+    ws = [torch.randn(64, device=DEV).bfloat16() for _ in range(3)]
+    x = torch.randn(3, 2, 64, device=DEV).bfloat16()
+    y = bd.DataParallelModule(ln, ws)(x)
+    for t in range(3):
+        ref = torch.nn.functional.layer_norm(x[t], (64,), ws[t], ln.bias, ln.eps)
+        assert torch.equal(y[t], ref)
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("N,K,m,T", [(1024, 4096, 1, 6), (4096, 14336, 1, 6), (4096, 4096, 3, 6), (1024, 8192, 1, 8), (512, 1024, 20, 3), (384, 512, 150, 2)])
 def test_mistral_shapes_six_tenants(kernel, N, K, m, T):

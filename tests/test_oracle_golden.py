@@ -104,6 +104,31 @@ def test_demo_modules(golden):
     assert np.array_equal(emb, bf(g["emb_out"]))
 
 
+@pytest.mark.parametrize("tag", ["bf16", "fp16"])
+@pytest.mark.parametrize("m", [1, 3])
+def test_tenant_leaves(golden, tag, m):
+    """DataParallelModule around lm_head (ragged vocab), embed_tokens and the HF RMSNorm, as run by the reference."""
+    g = golden("tenant_leaves.npz")
+    dec = bf if tag == "bf16" else (lambda b: np.asarray(b).view(np.float16).astype(np.float32))
+    ulp = 2.0 ** -8 if tag == "bf16" else 2.0 ** -11
+    pre = f"{tag}_m{m}_"
+    x = dec(g[pre + "x"])
+    ws = [dec(g[pre + f"head_w{t}"]) for t in range(3)]
+    ref = dec(g[pre + "logits"])
+    got = O.dataparallel_forward(x, ws, "linear", out=tag)
+    assert got.shape == ref.shape == (3, m, 75)
+    fill = np.float32(-3.3895313892515355e38) if tag == "bf16" else np.float32(-65504.0)
+    for t, v in enumerate((70, 75, 64)):
+        assert np.all(ref[t, :, v:] == fill) and np.array_equal(got[t, :, v:], ref[t, :, v:])
+        assert np.all(np.abs(got[t, :, :v] - ref[t, :, :v]) <= 2 * ulp * np.abs(ref[t, :, :v]) + 1e-6)
+    normed = O.dataparallel_forward(x, list(dec(g[pre + "norm_w"])), "rmsnorm", eps=float(g["eps"]), out=tag)
+    refn = dec(g[pre + "normed"])
+    assert np.all(np.abs(normed - refn) <= 2 * ulp * np.abs(refn) + 1e-6)
+    assert (normed == refn).mean() > 0.98
+    emb = O.dataparallel_forward(g[pre + "ids"], [dec(g[pre + f"emb_w{t}"]) for t in range(3)], "embedding", out=tag)
+    assert np.array_equal(emb, dec(g[pre + "emb_out"]))
+
+
 def test_fold_matches_load_diff(golden):
     import torch
 
