@@ -72,6 +72,8 @@ def _load() -> ctypes.CDLL:
 
 
 lib = _load()
+if os.environ.get("BD_DBG_FLAGS"):  # bring-up knob (see bd_debug_set_flags); never set in normal use
+    lib.bd_debug_set_flags(int(os.environ["BD_DBG_FLAGS"]), 0)
 
 
 def check(status: int) -> None:

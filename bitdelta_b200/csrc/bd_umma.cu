@@ -218,6 +218,7 @@ __device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return
 // Hardware named barriers (ids 0..15): far cheaper than mbarriers.  id 0 = __syncthreads, 1 = epilogue, 2 = release of the
 // unpack group, kBarAFull0 + b = "A buffer b is written" (unpack warps + permute warp arrive, the MMA warp syncs).
 constexpr int kBarAFull0 = 4;
+constexpr int kBarTmemReady = 3;  // every warp but the TMA producer: tensor memory allocated, activation tiles zeroed
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -360,17 +361,25 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     mbar_init(&bar_dfull, 1);
     fence_barrier_init();
   }
-  if (warp == kWarpMma) tmem_alloc(&tmem_base_slot, kTmemCols);
   if (threadIdx.x == 0) s_released = 0;
-  // zero the permuted-activation tiles once: rows >= m of every tenant tile stay zero for the whole kernel
-  for (uint32_t i = threadIdx.x * 16; i < a.n_abuf * a.xp_buf_bytes; i += kThreads * 16)
-    *reinterpret_cast<uint4*>(smem + a.off_xp + i) = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  __syncthreads();  // mbarriers initialised
+  // The TMA producer needs nothing else: it starts requesting the first weight / sign stages right away, while the other
+  // warps allocate tensor memory and zero the permuted-activation tiles and rendezvous without it.
+  if (warp != kWarpProducer || (a.dbg_flags & 4)) {
+    if (warp == kWarpMma) tmem_alloc(&tmem_base_slot, kTmemCols);
+    // zero the permuted-activation tiles once: rows >= m of every tenant tile stay zero for the whole kernel
+    const bool all = (a.dbg_flags & 4) != 0;
+    const uint32_t part = all ? threadIdx.x : threadIdx.x - (warp > kWarpProducer ? 32u : 0u);
+    const uint32_t nparts = all ? kThreads : kThreads - 32;
+    for (uint32_t i = part * 16; i < a.n_abuf * a.xp_buf_bytes; i += nparts * 16)
+      *reinterpret_cast<uint4*>(smem + a.off_xp + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    named_bar_sync(kBarTmemReady, (int)nparts);
+    tc_fence_after();
+  }
   if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 1] = clock64();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = (warp != kWarpProducer) ? tmem_base_slot : 0u;
   // TMEM columns: [0, ntb) base accumulator, [ntb, ntb + T*mp) delta accumulator, then the A-operand buffers
   const uint32_t col_dbase = 0, col_ddelta = a.ntb;
   const uint32_t a_cols_per_buf = (uint32_t)a.T * a.a_cols_tenant;
@@ -863,7 +872,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 long long* g_trace_buf = nullptr;
-int g_dbg_flags = 0;  // bit 0 = stream only, bit 1 = force the 16-bit delta path
+int g_dbg_flags = 0;  // bit 0 = stream only, bit 1 = force the 16-bit delta path, bit 2 = producer waits for the TMEM rendezvous
 
 struct DeviceInfo {
   int sms = 0, smem_optin = 0, cc_major = 0;
@@ -945,6 +954,14 @@ UmmaPlan choose_plan(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, bool
 
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  // The driver entry point needs a current context on the calling thread; a thread that has only ever had its device
+  // *selected* (e.g. PyTorch's autograd worker) has none until its first runtime call that touches the device.
+  static thread_local int ctx_dev = -1;
+  int cur_dev = -1;
+  if (cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev != ctx_dev) {
+    (void)cudaFree(nullptr);
+    ctx_dev = cur_dev;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(BD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};

@@ -97,6 +97,38 @@ def _fused_forward_grouped(x: torch.Tensor, weights, masks_list, coeffs, T: int,
     return ys
 
 
+class _BinaryDiffFunction(torch.autograd.Function):
+    """Scale distillation through the fused op (reference train.py:60-97 trains ``coeff`` through ``BinaryDiff.forward``).
+
+    The reference's ``binary_bmm`` output has no ``grad_fn``, so autograd sees ``y = x @ base + coeff * D`` with ``D`` a
+    constant:  d/dcoeff = sum(grad_y * D),  d/dx = grad_y @ base.T  (the delta term does NOT back-propagate into x).
+    ``delta_grad_x=True`` adds the true term ``coeff * grad_y @ sign.T`` instead of dropping it.
+    """
+
+    @staticmethod
+    def forward(ctx, rows, w_nk, mask, coeff, kernel, delta_grad_x):
+        ctx.save_for_backward(rows, w_nk, mask, coeff)
+        ctx.kernel, ctx.delta_grad_x = kernel, delta_grad_x
+        return _fused_forward(rows, w_nk, mask, coeff, 1, kernel)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        from .binary_gemm_kernel import binary_bmm, unpack
+
+        rows, w_nk, mask, coeff = ctx.saved_tensors
+        grad_y = grad_y.contiguous()
+        grad_rows = grad_coeff = None
+        if ctx.needs_input_grad[3]:
+            d = binary_bmm(rows, mask[None])  # x . sign, fp32 accumulate, one rounding (the reference's Delta-branch output)
+            grad_coeff = (grad_y.float() * d.float()).sum().to(coeff.dtype).reshape(coeff.shape)
+        if ctx.needs_input_grad[0]:
+            grad_rows = torch.matmul(grad_y, w_nk)  # plain library GEMM: [1,M,N] @ [N,K]
+            if ctx.delta_grad_x:
+                sign = (unpack(mask).to(rows.dtype) * 2 - 1)  # [K, N]
+                grad_rows = grad_rows + (coeff.float() * torch.matmul(grad_y, sign.t()).float()).to(rows.dtype)
+        return grad_rows, None, None, grad_coeff, None, None
+
+
 class BinaryDiff(nn.Module):
     """16-bit base weight + 1-bit delta linear layer (reference ``BinaryDiff``, diff.py:8-39).
 
@@ -106,6 +138,7 @@ class BinaryDiff(nn.Module):
     """
 
     kernel = "auto"
+    delta_grad_x = False  # reference behaviour: the delta branch carries no gradient w.r.t. the activations
 
     def __init__(self, base: torch.Tensor, finetune: torch.Tensor):
         super().__init__()
@@ -153,7 +186,10 @@ class BinaryDiff(nn.Module):
         # [B, seq, in] @ [in, out] + coeff * ([B, seq, in] @ sign[in, out])   (diff.py:33-39)
         lead = x.shape[:-1]
         rows = x.reshape(1, -1, x.shape[-1]).contiguous()
-        y = _fused_forward(rows, self._weight_nk(), self.mask, self.coeff, 1, self.kernel)
+        if torch.is_grad_enabled() and (rows.requires_grad or self.coeff.requires_grad):
+            y = _BinaryDiffFunction.apply(rows, self._weight_nk(), self.mask, self.coeff, self.kernel, self.delta_grad_x)
+        else:
+            y = _fused_forward(rows, self._weight_nk(), self.mask, self.coeff, 1, self.kernel)
         return y.reshape(*lead, y.shape[-1])
 
 

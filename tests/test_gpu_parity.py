@@ -308,6 +308,80 @@ def test_dataparallel_reference_vectors(golden):
     assert np.array_equal(to_np(out), bf(g["emb_out"]))
 
 
+@pytest.mark.parametrize("delta_grad_x", [False, True])
+def test_binarydiff_scale_gradients(delta_grad_x):
+    """Scale distillation (train.py:60-97): gradients of the fused op against autograd over the reference's composition
+    y = x @ base + coeff * D, where D = binary_bmm(x, mask) is a constant for autograd (no grad_fn in the reference)."""
+    torch.manual_seed(11)
+    N, K, M = 256, 512, 24
+    base = (torch.randn(N, K, device=DEV) * 0.02).bfloat16()
+    fine = (base.float() + torch.randn(N, K, device=DEV) * 0.002).bfloat16()
+    mod = bd.BinaryDiff(base, fine)
+    mod.delta_grad_x = delta_grad_x
+    x = torch.randn(2, M // 2, K, device=DEV).bfloat16().requires_grad_(True)
+    gy = torch.randn(2, M // 2, N, device=DEV).bfloat16()
+    y = mod(x)
+    assert y.grad_fn is not None
+    y.backward(gy)
+    g_coeff, g_x = mod.coeff.grad.clone(), x.grad.clone()
+    # fp64 autograd over the same composition
+    sign = (bd.unpack(mod.mask).double() * 2 - 1)  # [K, N]
+    xr = x.detach().double().requires_grad_(True)
+    cr = mod.coeff.detach().double().requires_grad_(True)
+    d = xr @ sign
+    yr = xr @ base.double().T + cr * (d if delta_grad_x else d.detach())
+    yr.backward(gy.double())
+    assert abs(g_coeff.item() - cr.grad.item()) <= 2e-3 * abs(cr.grad.item()) + 1e-3 * (gy.double().abs() * d.detach().abs()).sum().item() ** 0.5
+    rel = ((g_x.double() - xr.grad).abs().mean() / xr.grad.abs().mean()).item()
+    assert rel < 4e-3, rel
+    with torch.no_grad():
+        assert mod(x).grad_fn is None
+
+
+def test_tiny_llama_multi_tenant_logits_match_reference_fold(golden):
+    """Model level: a 2-layer Llama served through register_diff_compress (fused 1-bit-delta linears + the native
+    per-tenant leaves) must reproduce the logits the REFERENCE computed after folding the same diff.pt into the weights
+    (load_diff, diff.py:81-106; recorded by gen_golden.py).  The two differ only by the bf16 rounding of the folded weight."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from bitdelta_b200 import _lib
+    from bitdelta_b200 import demo_backend as db
+
+    g = golden("tiny_llama.npz")
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=96, max_position_embeddings=64, tie_word_embeddings=False)
+    sd = {k[len("basesd::"):]: t_bf16(g[k]) for k in g.files if k.startswith("basesd::")}
+    model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    path = os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt")
+    ckpts = []
+    for _ in range(2):  # two tenants carrying the same delta: row t of the batch is served by checkpoint t
+        d = torch.load(path, weights_only=False)
+        ckpts.append({k: (v.detach().to(DEV).to(torch.bfloat16) if v.is_floating_point() else v.to(DEV)) for k, v in d.items()})
+    db.cached_modules.clear()
+    try:
+        db.register_diff_compress(model, ckpts)
+        assert db.fuse_sibling_projections(model) == 4
+        assert isinstance(model.lm_head, db.DataParallelModule) and isinstance(model.model.norm, db.DataParallelModule)
+        ids = torch.from_numpy(g["ids"]).to(DEV)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            logits = model(ids).logits.float().cpu().numpy()
+        assert _lib.launch_count() > n0
+        ref = g["folded_logits"]
+        assert logits.shape == ref.shape
+        assert O.rel_mean_abs_err(logits, ref) < 3e-2
+        assert (logits.argmax(-1) == ref.argmax(-1)).mean() >= 0.9
+        with torch.no_grad():  # decode-size call: one token per tenant, lm_head on the native ragged kernel
+            one = model(ids[:, :1]).logits.float().cpu().numpy()
+        assert O.rel_mean_abs_err(one, ref[:, :1]) < 3e-2
+    finally:
+        db.unregister_diff_compress(model)
+        db.cached_modules.clear()
+    assert isinstance(model.lm_head, torch.nn.Linear)
+
+
 def t_16(bits: np.ndarray, tag: str) -> torch.Tensor:
     return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16 if tag == "bf16" else torch.float16)
 

@@ -38,12 +38,9 @@ k = t[63]
 print(f"kernel (CTA 0): entry->setup {k[1]-k[0]} cyc, setup->first TMA {t0-k[1]}, first TMA->last unit done {k[2]-t0}, last epilogue {k[3]-k[2]}, ->teardown {k[4]-k[3]}; total {k[4]-k[0]} cyc = {(k[9]-k[8])/1e3:.2f} us (globaltimer)")
 names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived"]
 print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
-print("unit " + " ".join(n.rjust(9) for n in names) + "   | unpack  mma_issue  afull->aempty(+2)")
+print("unit " + " ".join(n.rjust(9) for n in names))
 for it in range(64):
-    if t[it, 0].item() == 0:
+    if not any(t[it, s].item() for s in range(12)):
         break
-    row = [t[it, s].item() - t0 for s in range(12)]
-    extra = ""
-    if it + 2 < 64 and t[it + 2, 1].item():
-        extra = f"{row[4]-row[1]:8d} {row[7]-row[6]:9d} {t[it+2,1].item()-t0-row[6]:9d}"
-    print(f"{it:4d} " + " ".join(str(v).rjust(9) for v in row) + "   | " + extra)
+    row = [(t[it, s].item() - t0) if t[it, s].item() else -1 for s in range(12)]
+    print(f"{it:4d} " + " ".join(str(v).rjust(9) for v in row))
