@@ -336,6 +336,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // the unpack warps.
   const int xjobs = DELTA8 ? a.rows * 16 : a.rows * 8;
   const bool xperm_shared = xjobs > kXpermWarps * 32 * 2;
+  // Decode (8-bit delta path, small row counts): the two unpack warps of a TMEM lane quadrant take ALTERNATE units (all
+  // tenants of a unit each) instead of splitting the tenants of every unit.  tcgen05.st drains at ~16 B/clk per quadrant
+  // (measured: 24 KB per quadrant and round in ~1640 cycles), which at 6 tenants is most of the per-unit HBM time; with
+  // alternating units one warp's stores drain while the other warp is in its per-unit synchronisation (release check,
+  // fences, wait::st, barrier arrive, loop), instead of both warps paying that with the store port idle.
+  const bool alt_units = DELTA8 && !xperm_shared && !(a.dbg_flags & 8);
+  const int afull_threads = alt_units ? (kUnpackWarps / 2 + kXpermWarps + 1) * 32 : kAFullThreads;
 
   // Programmatic dependent launch: let the next kernel of the stream be scheduled as soon as SMs free up.  Its CTAs run
   // their prologue and prefetch their first weight / sign tiles (static data) while this grid drains; only its
@@ -506,7 +513,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       // "A buffer written" is a hardware named barrier (8 unpack warps + permute warp arrive, this warp syncs).  It also
       // implies that the stage has landed: those warps only get there after the stage's mbarrier completed.  mbarrier
       // operations are slow and serialised per SM, so every role touches as few of them as it can.
-      named_bar_sync(kBarAFull0 + ab.idx, kAFullThreads);
+      named_bar_sync(kBarAFull0 + ab.idx, afull_threads);
       tc_fence_after();
       Ring st_next = st;
       st_next.advance(a.stages);
@@ -571,7 +578,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         fence_proxy_async();
       }
       if (warp == kWarpXperm0 && lane == 0) trace_mark<TRACE>(a, u - u_begin, 10);
-      named_bar_arrive(kBarAFull0 + ab.idx, kAFullThreads);
+      named_bar_arrive(kBarAFull0 + ab.idx, afull_threads);
       st.advance(a.stages);
       ab.advance(a.n_abuf);
     }
@@ -606,20 +613,20 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
     uint32_t dphase = 0;
     // Sign words of one unit -> +-1.0 operand registers -> TMEM A buffer `abi` (this warp's tenants, this thread's row).
-    auto unpack_unit = [&](const uint8_t* sp, int abi) {
+    auto unpack_unit = [&](const uint8_t* sp, int abi, int tfirst, int tstep) {
       const uint32_t* mw = reinterpret_cast<const uint32_t*>(sp + a.off_masks) + row;
       const uint32_t ta = tmem_base + lane_addr + col_abuf0 + abi * a_cols_per_buf;
 #pragma unroll 1
-      for (int t0 = grp; t0 < a.T; t0 += 6) {  // up to three tenants (t0, t0+2, t0+4) per pass
+      for (int t0 = tfirst; t0 < a.T; t0 += 3 * tstep) {  // up to three tenants (t0, t0+tstep, t0+2*tstep) per pass
         uint32_t wv[3][kBlockK / 32];
 #pragma unroll
         for (int q = 0; q < 3; ++q)
 #pragma unroll
           for (int jj = 0; jj < kBlockK / 32; ++jj)
-            wv[q][jj] = (t0 + 2 * q < a.T) ? mw[((t0 + 2 * q) * (kBlockK / 32) + jj) * kTileN] : 0u;
+            wv[q][jj] = (t0 + tstep * q < a.T) ? mw[((t0 + tstep * q) * (kBlockK / 32) + jj) * kTileN] : 0u;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          const int t = t0 + 2 * q;
+          const int t = t0 + tstep * q;
           if (t >= a.T) break;
 #pragma unroll
           for (int jj = 0; jj < kBlockK / 32; ++jj) {
@@ -666,6 +673,27 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       const bool tr = (uw == 0 && lane == 0);
       // The sync warp waits on the mbarriers for the whole group and publishes released units in s_released.
       if (tr) trace_mark<TRACE>(a, it, 0);
+      if (alt_units) {
+        // this warp's unit of the round (at most one: g <= 2): the one whose index has this warp group's parity
+        const int my = ((it & 1) == grp) ? 0 : 1;
+        if (my < g) {
+          wait_released(&s_released, it + my);
+          tc_fence_after();
+          if (tr) trace_mark<TRACE>(a, it, 1);
+          Ring st_i = st, ab_i = ab;
+          if (my) { st_i.advance(a.stages); ab_i.advance(a.n_abuf); }
+          if (!(a.dbg_flags & 1)) {
+            unpack_unit(smem + (size_t)st_i.idx * a.stage_bytes, ab_i.idx, 0, 1);
+            if (tr) trace_mark<TRACE>(a, it, 3);
+            tc_wait_st();
+          }
+          tc_fence_before();
+          if (tr) trace_mark<TRACE>(a, it, 4);
+          named_bar_arrive(kBarAFull0 + ab_i.idx, afull_threads);  // this warp's rows of A buffer ab_i.idx are written
+          if (tr) trace_mark<TRACE>(a, it, 11);
+        }
+        for (int i = 0; i < g; ++i) { st.advance(a.stages); ab.advance(a.n_abuf); }
+      } else {
       wait_released(&s_released, it + g - 1);
       tc_fence_after();
       if (tr) trace_mark<TRACE>(a, it, 1);
@@ -677,7 +705,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
             uint8_t* xp = smem + a.off_xp + (size_t)ab_i.idx * a.xp_buf_bytes;
             for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) xperm_job(sp + a.off_x, xp, job);
           }
-          unpack_unit(sp, ab_i.idx);
+          unpack_unit(sp, ab_i.idx, grp, 2);
           st_i.advance(a.stages);
           ab_i.advance(a.n_abuf);
         }
@@ -689,11 +717,12 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       if (tr) trace_mark<TRACE>(a, it, 4);
       if (uw == kUnpackWarps - 1 && lane == 0) trace_mark<TRACE>(a, it, 9);
       for (int i = 0; i < g; ++i) {
-        named_bar_arrive(kBarAFull0 + ab.idx, kAFullThreads);  // this warp's part of A buffer ab.idx is written
+        named_bar_arrive(kBarAFull0 + ab.idx, afull_threads);  // this warp's part of A buffer ab.idx is written
         st.advance(a.stages);
         ab.advance(a.n_abuf);
       }
       if (tr) trace_mark<TRACE>(a, it, 11);
+      }
       u += g;
       kb += g - 1;  // kb = K block of the last unit of the round (the epilogue below looks at it)
       if ((a.dbg_flags & 1) && seg_last) {
@@ -872,7 +901,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 long long* g_trace_buf = nullptr;
-int g_dbg_flags = 0;  // bit 0 = stream only, bit 1 = force the 16-bit delta path, bit 2 = producer waits for the TMEM rendezvous
+int g_dbg_flags = 0;  // bit 0 = stream only, bit 1 = force the 16-bit delta path, bit 2 = producer waits for the TMEM rendezvous, bit 3 = unpack warps split tenants (not units)
 
 struct DeviceInfo {
   int sms = 0, smem_optin = 0, cc_major = 0;
