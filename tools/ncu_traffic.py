@@ -2,16 +2,24 @@
 """Turns an ncu raw CSV of one decoder layer's 7 fused launches (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum)
 into profiles/traffic.json.  usage: ncu_traffic.py <raw.csv> <out.json>"""
 import csv, json, sys
-rows = list(csv.reader(open(sys.argv[1])))
+rows = [r for r in csv.reader(open(sys.argv[1])) if r and not r[0].startswith("==")]
 start = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 h = rows[start]
 recs = {}
-for r in rows[start + 1:]:
-    if len(r) < len(h):
-        continue
-    d = dict(zip(h, r))
-    k = int(d["ID"])
-    recs.setdefault(k, {})[d["Metric Name"]] = (float(d["Metric Value"]), d["Metric Unit"])
+WANT = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum")
+if "Metric Name" in h:  # long format (default --csv): one row per (launch, metric)
+    for r in rows[start + 1:]:
+        if len(r) < len(h) or not r[0].strip().isdigit():
+            continue
+        d = dict(zip(h, r))
+        recs.setdefault(int(d["ID"]), {})[d["Metric Name"]] = (float(d["Metric Value"].replace(",", "")), d["Metric Unit"])
+else:  # wide format (--page raw): one row per launch, a units row under the header
+    units = rows[start + 1]
+    col = {n: i for i, n in enumerate(h)}
+    for r in rows[start + 2:]:
+        if len(r) < len(h) or not r[0].strip().isdigit():
+            continue
+        recs[int(r[0])] = {m: (float(r[col[m]].replace(",", "")), units[col[m]]) for m in WANT}
 names7 = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
 names4 = ["q+k+v_proj (grouped)", "o_proj", "gate+up_proj (grouped)", "down_proj"]
 names = names4 if len(recs) <= 4 else names7
