@@ -41,6 +41,22 @@ def test_errors_are_status_codes_with_messages():
     assert rc == -1 and b"w is required" in _lib.lib.bd_last_error()
     rc = _lib.lib.bd_binary_bmm(16, 16, 16, 5, 1, 1, 32, 8, 0, None, 0, 0, None)
     assert rc == -2
+    # per-tenant leaves: same convention (validation before any CUDA call)
+    import ctypes
+
+    ptrs = (ctypes.c_void_p * 2)(256, 512)
+    n_out = (ctypes.c_int64 * 2)(8, 8)
+    rc = _lib.lib.bd_tenant_linear(256, ptrs, n_out, None, 256, 0, 2, 5, 64, 8, None)
+    assert rc == -1 and b"rows per tenant" in _lib.lib.bd_last_error()
+    rc = _lib.lib.bd_tenant_linear(256, ptrs, n_out, None, 256, 0, 2, 1, 60, 8, None)
+    assert rc == -1 and b"multiple of 8" in _lib.lib.bd_last_error()
+    n_bad = (ctypes.c_int64 * 2)(8, 9)
+    rc = _lib.lib.bd_tenant_linear(256, ptrs, n_bad, None, 256, 0, 2, 1, 64, 8, None)
+    assert rc == -1 and b"out of range" in _lib.lib.bd_last_error()
+    rc = _lib.lib.bd_tenant_rmsnorm(256, ptrs, 256, 2, 2, 1, 64, 1e-5, None)
+    assert rc == -1 and b"dtype" in _lib.lib.bd_last_error()
+    rc = _lib.lib.bd_tenant_embed(None, ptrs, n_out, 256, 0, 2, 1, 64, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.bd_last_error()
     assert _lib.lib.bd_workspace_bytes(6, 14336) >= 8192
     assert _lib.lib.bd_select_kernel(0, 6, 1, 4096, 4096, 1) in (1, 2)
     assert _lib.lib.bd_select_kernel(0, 1, 1, 32, 50, 1) == 1  # odd shapes go to the general kernel

@@ -166,3 +166,27 @@ def test_register_unregister_on_host_modules():
     with pytest.raises(AssertionError, match="Only support linear layer"):
         bd.register_diff_compress(M(), [{"norm.mask": torch.zeros(2, 64, dtype=torch.int32), "norm.coeff": torch.tensor(1.0)}])
     bd.demo_backend.cached_modules.clear()
+
+
+@pytest.mark.parametrize("tag", ["bf16", "fp16"])
+def test_dataparallel_host_path_matches_reference_vectors(golden, tag):
+    """On host tensors DataParallelModule runs the reference's generic loop (the native kernels are CUDA-only): its
+    outputs must equal the reference module's (tests/golden/gen_golden.py::gen_tenant_leaves) bit for bit."""
+    from transformers.models.llama.modeling_llama import LlamaRMSNorm
+
+    g = golden("tenant_leaves.npz")
+    dt = torch.bfloat16 if tag == "bf16" else torch.float16
+    t16 = lambda b: torch.from_numpy(b.view(np.int16).copy()).view(dt)  # noqa: E731
+    bits = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    for m in (1, 3):
+        pre = f"{tag}_m{m}_"
+        x = t16(g[pre + "x"])
+        head = torch.nn.Linear(256, 70, bias=False).to(dt)
+        with torch.no_grad():
+            logits = bd.DataParallelModule(head, [t16(g[pre + f"head_w{t}"]) for t in range(3)])(x)
+            normed = bd.DataParallelModule(LlamaRMSNorm(256, eps=float(g["eps"])).to(dt), [t16(w) for w in g[pre + "norm_w"]])(x)
+            emb = bd.DataParallelModule(torch.nn.Embedding(75, 256).to(dt), [t16(g[pre + f"emb_w{t}"]) for t in range(3)])(
+                torch.from_numpy(g[pre + "ids"]))
+        assert np.array_equal(bits(logits), g[pre + "logits"])
+        assert np.array_equal(bits(normed), g[pre + "normed"])
+        assert np.array_equal(bits(emb), g[pre + "emb_out"])
