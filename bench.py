@@ -69,23 +69,45 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
 
-    def start(self):
+    def start(self, wait_first: float = 3.0):
+        """Starts nvidia-smi -lms 20 and returns once its first sample has arrived (its start-up can take longer than a short
+        timed region), so the loop is sampling for the whole of the region that follows."""
+        import threading
+
+        self.lines = []
+        self._first = threading.Event()
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def reader():
+            for line in self.proc.stdout:
+                self.lines.append(line)
+                self._first.set()
+
+        self._thread = threading.Thread(target=reader, daemon=True)
+        self._thread.start()
+        self._first.wait(wait_first)
+
+    def mark(self):
+        """Drops the samples taken so far (idle GPU, warm-up): called right before the timed region."""
+        if self.proc is not None:
+            self.lines.clear()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
+        self._thread.join(timeout=2)
+        out = "".join(self.lines)
         sm, smax, reasons = [], [], set()
         for line in out.strip().splitlines():
             f = [s.strip() for s in line.split(",")]
@@ -246,12 +268,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             torch.cuda.synchronize(dev)
 
         # ---- device-resident timing -------------------------------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()  # returns once nvidia-smi delivers samples; the warm-up below keeps the GPU busy meanwhile
         for _ in range(args.warmup):
             graph.replay()
-        sampler = ClockSampler(local_rank)
         barrier()
         if rank == 0:
-            sampler.start()
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
