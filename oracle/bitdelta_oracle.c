@@ -73,6 +73,7 @@ void oracle_fwd_batched_bf16(const uint16_t* x, const uint16_t* w, const int32_t
             if (w) {
               const uint16_t* wr = w + n * K;
               const float* xr = xf + r * K;
+#pragma omp simd reduction(+ : acc)
               for (int64_t k = 0; k < K; ++k) acc += xr[k] * bf16_to_f32(wr[k]);
             }
             y[r * N + n] = acc;
