@@ -145,6 +145,7 @@ def cpu_layer_sample(threads: int = 0, reps: int = 1, seed: int = 0):
         coeff = np.full(TENANTS, 0.002, np.float32)
         probs.append((x, w, masks, coeff))
     cores = threads or C.max_threads()
+    threads = cores  # explicit: OpenMP's own default ignores the cgroup CPU quota
     C.fwd_batched_bf16(*probs[1], threads=threads)  # warm the thread pool / page in
     times = []
     for _ in range(reps):
