@@ -142,7 +142,9 @@ class SiblingGroup:
         self._outs = {}
 
     def forward_for(self, who, x):
-        key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, x.device)
+        # inference tensors (torch.inference_mode, which the reference's decode loop uses) carry no version counter
+        ver = 0 if x.is_inference() else x._version
+        key = (x.data_ptr(), ver, tuple(x.shape), x.dtype, x.device)
         if self._key != key or id(who) not in self._outs:
             T = who.mask.shape[0]
             ws = [m.module.weight if m.module.weight.is_contiguous() else m.module.weight.contiguous() for m in self.members]

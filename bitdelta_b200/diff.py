@@ -177,7 +177,7 @@ class BinaryDiff(nn.Module):
         w = self.base.t()
         if w.is_contiguous():
             return w
-        key = (self.base.data_ptr(), self.base._version, self.base.device)
+        key = (self.base.data_ptr(), 0 if self.base.is_inference() else self.base._version, self.base.device)
         if self._w_cache is None or self._w_cache[0] != key:
             self._w_cache = (key, w.contiguous())
         return self._w_cache[1]

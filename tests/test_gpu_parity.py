@@ -382,6 +382,54 @@ def test_tiny_llama_multi_tenant_logits_match_reference_fold(golden):
     assert isinstance(model.lm_head, torch.nn.Linear)
 
 
+def test_decode_loop_over_registered_model_matches_folded_model(golden):
+    """f-3: the greedy multi-tenant decode loop (demo_backend.py:190-258) over a model served through the fused modules must
+    produce the tokens HF's greedy generate produces on the model with the SAME diff folded into its weights (load_diff)."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from bitdelta_b200 import demo_backend as db
+
+    g = golden("tiny_llama.npz")
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=96, max_position_embeddings=64, tie_word_embeddings=False)
+    sd = {k[len("basesd::"):]: t_bf16(g[k]) for k in g.files if k.startswith("basesd::")}
+    path = os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt")
+    folded = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    folded.load_state_dict(sd)
+    bd.load_diff(folded, path)
+    folded = folded.to(DEV).eval()
+    model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    ckpts = []
+    for _ in range(2):
+        d = torch.load(path, weights_only=False)
+        ckpts.append({k: (v.detach().to(DEV).to(torch.bfloat16) if v.is_floating_point() else v.to(DEV)) for k, v in d.items()})
+    ids = torch.from_numpy(g["ids"]).to(DEV)[:, :8]
+    mask = torch.ones_like(ids)
+    n = 6
+    with torch.no_grad():
+        ref = folded.generate(ids, attention_mask=mask, max_new_tokens=n, do_sample=False, pad_token_id=0, eos_token_id=None)[:, 8:]
+        ref_logits = folded(ids).logits[:, -1].float()
+    db.cached_modules.clear()
+    try:
+        db.register_diff_compress(model, ckpts)
+        db.fuse_sibling_projections(model)
+        ours = bd.greedy_decode(model, ids, mask, n)
+    finally:
+        db.unregister_diff_compress(model)
+        db.cached_modules.clear()
+    assert ours.shape == (2, n)
+    # bf16 near-ties can flip an argmax between the folded and the unfolded arithmetic (and a flipped token changes the rest
+    # of a random-init model's sequence): require the first token to agree unless the top-2 margin is within bf16 noise
+    top2 = ref_logits.topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1]) / top2[:, 0].abs().clamp_min(1e-6)
+    for t in range(2):
+        if margin[t] > 0.05:
+            assert ours[t, 0] == ref[t, 0]
+    assert int(ours.min()) >= 0 and int(ours.max()) < 96  # never an index from the finfo.min padding
+
+
 def t_16(bits: np.ndarray, tag: str) -> torch.Tensor:
     return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16 if tag == "bf16" else torch.float16)
 
