@@ -129,12 +129,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_layer_sample(threads: int = 0, reps: int = 1, seed: int = 0):
-    """Times the oracle's C port on ONE Mistral decoder layer (7 linears, 6 tenants, 1 token each) on the host cores.
-    Returns (seconds per layer, cores used).  Only bench.py's baseline legs may execute oracle/ code."""
+def cpu_layer_problems(seed: int = 0):
+    """Synthetic operands of ONE Mistral decoder layer (7 linears, 6 tenants, 1 token each) for the CPU baseline."""
     import numpy as np
-
-    from oracle import c_oracle as C
 
     rng = np.random.default_rng(seed)
     probs = []
@@ -144,9 +141,21 @@ def cpu_layer_sample(threads: int = 0, reps: int = 1, seed: int = 0):
         masks = rng.integers(-(2**31), 2**31 - 1, (TENANTS, k // 32, n)).astype(np.int32)
         coeff = np.full(TENANTS, 0.002, np.float32)
         probs.append((x, w, masks, coeff))
+    return probs
+
+
+def cpu_layer_sample(threads: int = 0, reps: int = 1, seed: int = 0, probs=None):
+    """Times the oracle's C port on ONE Mistral decoder layer on the host cores.  Returns (seconds per layer, cores used).
+    Only bench.py's baseline legs may execute oracle/ code."""
+    from oracle import c_oracle as C
+
+    fresh = probs is None
+    if fresh:
+        probs = cpu_layer_problems(seed)
     cores = threads or C.max_threads()
     threads = cores  # explicit: OpenMP's own default ignores the cgroup CPU quota
-    C.fwd_batched_bf16(*probs[1], threads=threads)  # warm the thread pool / page in
+    if fresh:
+        C.fwd_batched_bf16(*probs[1], threads=threads)  # warm the thread pool / page in
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -160,13 +169,14 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     t_layers = []
+    probs = cpu_layer_problems(0)  # generated once (600 MB): a step is one pass of the C port over the layer's operands
     for i in range(args.warmup + args.steps):
-        t, cores = cpu_layer_sample(threads=0, reps=2, seed=i)  # best of 2 passes: the first pass over freshly generated arrays pays first-touch costs
+        t, cores = cpu_layer_sample(threads=0, reps=1, probs=probs)
         if i >= args.warmup:
             t_layers.append(t)
     t_step = statistics.mean(t_layers) * LAYERS
     value = TENANTS / t_step
-    sample = f"1 of {LAYERS} decoder layers per step (7 linears x {TENANTS} tenants x 1 token), best of 2 passes, scaled x{LAYERS}"
+    sample = f"1 of {LAYERS} decoder layers per step (7 linears x {TENANTS} tenants x 1 token, operands resident), scaled x{LAYERS}"
     line = {
         "impl": "reference", "metric": "tokens/sec Mistral-7B+6delta batched decode (BinaryDiff linears)", "value": value,
         "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
