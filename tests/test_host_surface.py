@@ -190,3 +190,19 @@ def test_dataparallel_host_path_matches_reference_vectors(golden, tag):
         assert np.array_equal(bits(logits), g[pre + "logits"])
         assert np.array_equal(bits(normed), g[pre + "normed"])
         assert np.array_equal(bits(emb), g[pre + "emb_out"])
+
+
+def test_binarydiff_weight_view_cache_also_for_inference_tensors():
+    """BinaryDiff keeps the reference's base = W.T view; if a state_dict load made `base` a contiguous [K, N] buffer, the
+    [N, K] operand the kernel needs is rebuilt once and cached -- also under torch.inference_mode (no version counter)."""
+    base = (torch.randn(48, 96) * 0.02).bfloat16()
+    fine = (base.float() + torch.randn(48, 96) * 0.002).bfloat16()
+    m = bd.BinaryDiff(base, fine)
+    assert m._weight_nk().data_ptr() == base.data_ptr()  # zero-copy while the strides are the reference's
+    m.base = m.base.contiguous()
+    w = m._weight_nk()
+    assert w.is_contiguous() and torch.equal(w, base) and m._weight_nk() is w
+    with torch.inference_mode():
+        m2 = bd.BinaryDiff(base, fine)
+        m2.base = m2.base.contiguous()
+        assert torch.equal(m2._weight_nk(), base)
