@@ -217,47 +217,62 @@ class DiffCompressModule(nn.Module):
 cached_modules = {}
 
 
-def register_diff_compress(model, checkpoint_list):
-    """Wrap every leaf whose name appears in the checkpoints (reference :107-153).
-
-    ``<name>.weight`` in the checkpoint -> DataParallelModule over the tenants' full weights;
-    ``<name>.mask``   in the checkpoint -> DiffCompressModule over stacked masks ``[T,K/32,N]`` and coeffs ``[T]``
-    (stacked once, cached in ``cached_modules`` and popped from the per-tenant dicts to free memory).
-    """
-    for name, module in list(model.named_modules()):
-        if len(list(module.named_children())) != 0:
+def _leaf_sites(model):
+    """(path, leaf, parent module, attribute name) of every module without children, in traversal order."""
+    sites = []
+    for path, mod in model.named_modules():
+        if path == "" or next(mod.named_children(), None) is not None:
             continue
-        parent = model.get_submodule(".".join(name.split(".")[:-1]))
-        leaf = name.split(".")[-1]
-        if f"{name}.weight" in checkpoint_list[0]:
-            setattr(parent, leaf, DataParallelModule(module, [ckpt[f"{name}.weight"] for ckpt in checkpoint_list]))
-        elif f"{name}.mask" in checkpoint_list[0] or name in cached_modules:
-            assert isinstance(module, nn.Linear), "Only support linear layer"
-            if name not in cached_modules:
-                cached_modules[name] = (
-                    torch.stack([ckpt[f"{name}.mask"] for ckpt in checkpoint_list], dim=0).contiguous(),
-                    torch.stack([ckpt[f"{name}.coeff"] for ckpt in checkpoint_list], dim=0),
-                )
-                for ckpt in checkpoint_list:
-                    ckpt.pop(f"{name}.mask")
-                    ckpt.pop(f"{name}.coeff")
-                gc.collect()
-                if torch.cuda.is_available():
-                    torch.cuda.empty_cache()
-            setattr(parent, leaf, DiffCompressModule(module, cached_modules[name][0], cached_modules[name][1]))
+        parent_path, _, attr = path.rpartition(".")
+        sites.append((path, mod, model.get_submodule(parent_path), attr))
+    return sites
+
+
+def _stack_tenant_deltas(path, checkpoint_list):
+    """Masks [T,K/32,N] and coefficients [T] of one projection over all tenants, stacked once; the per-tenant entries are
+    removed from the checkpoint dicts so the memory is not held twice (reference :131-141)."""
+    masks = torch.stack([ck[f"{path}.mask"] for ck in checkpoint_list], dim=0).contiguous()
+    coeffs = torch.stack([ck[f"{path}.coeff"] for ck in checkpoint_list], dim=0)
+    for ck in checkpoint_list:
+        del ck[f"{path}.mask"], ck[f"{path}.coeff"]
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return masks, coeffs
+
+
+def register_diff_compress(model, checkpoint_list):
+    """Wrap every leaf whose path appears in the tenants' checkpoints (reference :107-153).
+
+    ``<path>.weight`` present -> ``DataParallelModule`` over the tenants' full weights (embed_tokens, norms, lm_head);
+    ``<path>.mask`` present (or stacked earlier and kept in ``cached_modules``) -> ``DiffCompressModule`` over the stacked
+    masks / coefficients.  Anything else is left alone.
+    """
+    first = checkpoint_list[0]
+    for path, leaf, parent, attr in _leaf_sites(model):
+        if f"{path}.weight" in first:
+            wrapped = DataParallelModule(leaf, [ck[f"{path}.weight"] for ck in checkpoint_list])
+        elif f"{path}.mask" in first or path in cached_modules:
+            assert isinstance(leaf, nn.Linear), "Only support linear layer"
+            if path not in cached_modules:
+                cached_modules[path] = _stack_tenant_deltas(path, checkpoint_list)
+            wrapped = DiffCompressModule(leaf, *cached_modules[path])
+        else:
+            continue
+        setattr(parent, attr, wrapped)
 
 
 def unregister_diff_compress(model):
-    """Undo register_diff_compress (reference :156-166)."""
-    for name, module in list(model.named_modules()):
-        if isinstance(module, DataParallelModule):
-            module.module.weight.data = module.original_weight
-            parent = model.get_submodule(".".join(name.split(".")[:-1]))
-            setattr(parent, name.split(".")[-1], module.module)
-        elif isinstance(module, DiffCompressModule):
-            module._group = None
-            parent = model.get_submodule(".".join(name.split(".")[:-1]))
-            setattr(parent, name.split(".")[-1], module.module)
+    """Put the original leaves back (reference :156-166); a DataParallelModule also restores the weight it swapped."""
+    for path, mod in list(model.named_modules()):
+        if isinstance(mod, DataParallelModule):
+            mod.module.weight.data = mod.original_weight
+        elif isinstance(mod, DiffCompressModule):
+            mod._group = None
+        else:
+            continue
+        parent_path, _, attr = path.rpartition(".")
+        setattr(model.get_submodule(parent_path), attr, mod.module)
 
 
 class DiffCompress:

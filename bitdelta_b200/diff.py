@@ -193,60 +193,75 @@ class BinaryDiff(nn.Module):
         return y.reshape(*lead, y.shape[-1])
 
 
+def _projection_sites(model):
+    """(parent module, parent path, child name) of every leaf the reference compresses: children whose name contains
+    ``proj`` under modules whose path contains ``mlp`` or ``self_attn`` (reference diff.py:60-64), in traversal order."""
+    sites = []
+    for path, parent in model.named_modules():
+        if "mlp" not in path and "self_attn" not in path:
+            continue
+        sites.extend((parent, path, child) for child, _ in parent.named_children() if "proj" in child)
+    return sites
+
+
+def _release_cached_memory():
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
 def compress_diff(base_model, finetuned_model, finetuned_compressed_model):
-    """Swap every ``*proj`` child of modules named ``*mlp*``/``*self_attn*`` for a BinaryDiff (reference diff.py:41-64)."""
-
-    def compress_submodule(name, subname, module, submodule):
-        target_device = submodule.weight.device
-        base_weight = base_model.get_submodule(f"{name}.{subname}").weight.detach().to(target_device)
-        finetuned_weight = finetuned_model.get_submodule(f"{name}.{subname}").weight.detach().to(target_device)
-        compressed = BinaryDiff(base=base_weight, finetune=finetuned_weight).to(target_device)
-        del submodule, base_weight
-        setattr(module, subname, None)
-        gc.collect()
-        if torch.cuda.is_available():
-            torch.cuda.empty_cache()
-        setattr(module, subname, compressed)
-
-    for name, module in finetuned_compressed_model.named_modules():
-        if "mlp" in name or "self_attn" in name:
-            for subname, submodule in module.named_children():
-                if "proj" in subname:
-                    compress_submodule(name, subname, module, submodule)
+    """Replace every projection of ``finetuned_compressed_model`` by ``BinaryDiff(base weight, fine-tuned weight)`` built on
+    the device the projection lives on (reference diff.py:41-64).  The dense layer is dropped before the compressed one is
+    attached so that a 7B model never holds both."""
+    for parent, path, child in _projection_sites(finetuned_compressed_model):
+        where = getattr(parent, child).weight.device
+        leaf = f"{path}.{child}"
+        w_base = base_model.get_submodule(leaf).weight.detach().to(where)
+        w_fine = finetuned_model.get_submodule(leaf).weight.detach().to(where)
+        replacement = BinaryDiff(base=w_base, finetune=w_fine).to(where)
+        del w_base, w_fine
+        setattr(parent, child, None)  # frees the dense projection
+        _release_cached_memory()
+        setattr(parent, child, replacement)
 
 
 def save_diff(finetuned_compressed_model, save_dir):
-    """Write ``diff.pt``: ``<module>.mask`` int32 [K/32,N], ``<module>.coeff`` fp32 0-dim, then every trainable parameter
-    under its own name -- byte-compatible with reference diff.py:66-79."""
-    diff_dict = {}
-    for name, module in finetuned_compressed_model.named_modules():
-        if isinstance(module, BinaryDiff):
-            diff_dict[name + ".mask"] = module.mask.cpu()
-            diff_dict[name + ".coeff"] = module.coeff.cpu()
-    for name, param in finetuned_compressed_model.named_parameters():
-        if param.requires_grad:
-            diff_dict[name] = param.cpu()
-    torch.save(diff_dict, save_dir)
+    """Write ``diff.pt`` in the reference's layout (diff.py:66-79): for every BinaryDiff ``<path>.mask`` (int32 [K/32,N]) and
+    ``<path>.coeff`` (fp32 0-dim), then every trainable parameter under its own name (which stores the coeffs again under
+    the same keys, and the full embeddings / norms / lm_head).  Everything is moved to the CPU; key order is the reference's."""
+    model = finetuned_compressed_model
+    entries = {}
+    for path, mod in model.named_modules():
+        if not isinstance(mod, BinaryDiff):
+            continue
+        entries[f"{path}.mask"] = mod.mask.cpu()
+        entries[f"{path}.coeff"] = mod.coeff.cpu()
+    entries.update((pname, p.cpu()) for pname, p in model.named_parameters() if p.requires_grad)
+    torch.save(entries, save_dir)
 
 
 @torch.no_grad()
 def load_diff(model, diff_dir):
-    """Fold a ``diff.pt`` into a dense model (reference diff.py:81-106): ``W += ((2*unpack(mask)-1)*coeff).T`` for
-    ``.mask`` entries (one device kernel, no [K,N] temporaries), replace ``.weight`` entries, add ``(A@B).T`` for LoRA pairs."""
-    device = model.device
-    diff_dict = torch.load(diff_dir, weights_only=False)
-    for name, module in model.named_modules():
-        if name + ".mask" in diff_dict:
-            coeff = diff_dict[name + ".coeff"].to(device)
-            mask = diff_dict[name + ".mask"].to(device)
-            fold_into(module.weight, mask, coeff)
-        elif name + ".weight" in diff_dict:
-            module.weight = nn.Parameter(diff_dict[name + ".weight"].to(device).to(module.weight.dtype))
-        elif name + ".A" in diff_dict:
-            A = diff_dict[name + ".A"].to(device)
-            B = diff_dict[name + ".B"].to(device)
-            module.weight.add_((A @ B).T.to(module.weight.dtype))
-    model.config.vocab_size = model.lm_head.weight.size(0)
+    """Fold a ``diff.pt`` into a dense model (reference diff.py:81-106).  Per module path: a ``.mask`` entry adds
+    ``((2*unpack(mask)-1)*coeff).T`` to the weight (one device kernel, no [K,N] temporaries); a ``.weight`` entry replaces
+    the parameter (cast to the model's dtype); an ``.A``/``.B`` LoRA pair adds ``(A@B).T``.  The config's vocabulary size
+    follows the (possibly replaced) lm_head."""
+    where = model.device
+    stored = torch.load(diff_dir, weights_only=False)
+
+    def fetch(key):
+        return stored[key].to(where)
+
+    for path, mod in model.named_modules():
+        if f"{path}.mask" in stored:
+            fold_into(mod.weight, fetch(f"{path}.mask"), fetch(f"{path}.coeff"))
+        elif f"{path}.weight" in stored:
+            mod.weight = nn.Parameter(fetch(f"{path}.weight").to(mod.weight.dtype))
+        elif f"{path}.A" in stored:
+            low_rank = fetch(f"{path}.A") @ fetch(f"{path}.B")
+            mod.weight.add_(low_rank.T.to(mod.weight.dtype))
+    model.config.vocab_size = model.lm_head.weight.shape[0]
 
 
 @torch.no_grad()
@@ -266,14 +281,12 @@ def fold_into(weight: torch.Tensor, mask: torch.Tensor, coeff: torch.Tensor) -> 
 
 
 def save_full_model(base_model_name, finetuned_model_name, diff_dir, save_dir, device):
-    """Reference diff.py:108-116: load the base model, fold the diff, save model + tokenizer."""
+    """Materialise the fine-tuned model from base + ``diff.pt`` and save it with the fine-tune's tokenizer (diff.py:108-116)."""
     import transformers
 
-    base_model = transformers.AutoModelForCausalLM.from_pretrained(
-        base_model_name, torch_dtype=torch.bfloat16, low_cpu_mem_usage=True
-    ).to(device)
-    tokenizer = transformers.AutoTokenizer.from_pretrained(finetuned_model_name)
-    load_diff(base_model, diff_dir)
-    base_model.save_pretrained(save_dir)
-    tokenizer.save_pretrained(save_dir)
-    del base_model
+    dense = transformers.AutoModelForCausalLM.from_pretrained(base_model_name, torch_dtype=torch.bfloat16, low_cpu_mem_usage=True)
+    dense = dense.to(device)
+    load_diff(dense, diff_dir)
+    dense.save_pretrained(save_dir)
+    transformers.AutoTokenizer.from_pretrained(finetuned_model_name).save_pretrained(save_dir)
+    del dense

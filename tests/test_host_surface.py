@@ -206,3 +206,35 @@ def test_binarydiff_weight_view_cache_also_for_inference_tensors():
         m2 = bd.BinaryDiff(base, fine)
         m2.base = m2.base.contiguous()
         assert torch.equal(m2._weight_nk(), base)
+
+
+def test_register_unregister_on_nested_hf_model(golden):
+    """The same wrap / unwrap over a real (2-layer) HF Llama and the reference's own diff.pt, on the host: every projection
+    becomes a DiffCompressModule with stacked [T, K/32, N] masks, every full-precision leaf a DataParallelModule, and
+    unregister restores the original modules and weights; a second register re-uses the cached stacks."""
+    from bitdelta_b200 import demo_backend as db
+
+    g, cfg, model = _tiny_models(golden)
+    path = os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt")
+    before = {n: p.data_ptr() for n, p in model.named_parameters()}
+    db.cached_modules.clear()
+    try:
+        for round_ in range(2):
+            ckpts = [torch.load(path, weights_only=False) for _ in range(3)]
+            db.register_diff_compress(model, ckpts)
+            assert db.fuse_sibling_projections(model) == 4
+            kinds = {n: type(m).__name__ for n, m in model.named_modules()}
+            assert kinds["model.layers.1.mlp.down_proj"] == "DiffCompressModule" and kinds["lm_head"] == "DataParallelModule"
+            assert kinds["model.embed_tokens"] == "DataParallelModule" and kinds["model.layers.0.input_layernorm"] == "DataParallelModule"
+            q = model.model.layers[0].self_attn.q_proj
+            assert q.mask.shape == (3, 2, 64) and q.coeff.shape == (3,) and q._group is not None
+            assert len(db.cached_modules) == 14
+            # entries are removed from the tenant dicts only when they are stacked, i.e. on the first register (reference :131-141)
+            assert ("model.layers.0.self_attn.q_proj.mask" in ckpts[0]) == (round_ == 1)
+            db.unregister_diff_compress(model)
+            assert isinstance(model.lm_head, torch.nn.Linear) and isinstance(model.model.layers[0].self_attn.q_proj, torch.nn.Linear)
+            assert {n: p.data_ptr() for n, p in model.named_parameters()} == before
+            if round_ == 0:  # the reference's cache: the next register finds the stacks although the fresh dicts carry them again
+                assert set(db.cached_modules) == {n for n, k in kinds.items() if k == "DiffCompressModule"}
+    finally:
+        db.cached_modules.clear()
