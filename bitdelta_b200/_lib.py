@@ -13,6 +13,11 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libbitdelta_b200.so")
+# tools/ (kernel A/B runs, the clock64 trace) opt into the separately built bring-up library; the release library has
+# neither the knobs nor the entry points, so nothing in the environment can change what a forward computes.
+BRINGUP = os.environ.get("BD_BRINGUP_LIB") == "1"
+if BRINGUP:
+    LIB_PATH = os.path.join(_PKG, "libbitdelta_b200_bringup.so")
 
 BD_BF16, BD_FP16, BD_FP32 = 0, 1, 2
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_UMMA = 0, 1, 2
@@ -25,7 +30,7 @@ EXPORTS = [
     "bd_compress", "bd_fold",
     "bd_binary_bmm", "bd_binarydiff_fwd_batched", "bd_binarydiff_fwd_grouped",
     "bd_tenant_linear", "bd_tenant_rmsnorm", "bd_tenant_embed",
-    "bd_workspace_bytes", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags",
+    "bd_workspace_bytes", "bd_select_kernel",
 ]
 
 
@@ -60,20 +65,19 @@ def _load() -> ctypes.CDLL:
     lib.bd_workspace_bytes.argtypes = [i64, i64]
     lib.bd_workspace_bytes.restype = sz
     lib.bd_select_kernel.argtypes = [i32, i64, i64, i64, i64, i32]
-    lib.bd_debug_set_trace.argtypes = [vp]
-    lib.bd_debug_set_trace.restype = None
-    lib.bd_debug_set_flags.argtypes = [i32, i32]
-    lib.bd_debug_set_flags.restype = None
+    if BRINGUP:
+        lib.bd_debug_set_trace.argtypes = [vp]
+        lib.bd_debug_set_trace.restype = None
+        lib.bd_debug_set_flags.argtypes = [i32, i32]
+        lib.bd_debug_set_flags.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if fn.restype is c.c_int and name not in ("bd_abi_version", "bd_select_kernel", "bd_debug_set_trace", "bd_debug_set_flags"):
+        if fn.restype is c.c_int and name not in ("bd_abi_version", "bd_select_kernel"):
             fn.restype = i32
     return lib
 
 
 lib = _load()
-if os.environ.get("BD_DBG_FLAGS"):  # bring-up knob (see bd_debug_set_flags); never set in normal use
-    lib.bd_debug_set_flags(int(os.environ["BD_DBG_FLAGS"]), 0)
 
 
 def check(status: int) -> None:

@@ -1,6 +1,6 @@
 """Builds libbitdelta_b200.so in-tree with nvcc for sm_100a (no torch, no JIT cache: the .so travels with the repo).
 
-    python bitdelta_b200/build.py [--force] [-v]      (run as a script: importing the package requires the built library)
+    python bitdelta_b200/build.py [--force] [-v] [--bringup]      (run as a script: importing the package requires the built library)
 """
 from __future__ import annotations
 
@@ -12,6 +12,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libbitdelta_b200.so")
+OUT_BRINGUP = os.path.join(PKG, "libbitdelta_b200_bringup.so")  # -DBD_BRINGUP: trace + A/B knobs, for tools/ only
 SOURCES = ["bd_api.cu", "bd_codec.cu", "bd_simt.cu", "bd_umma.cu", "bd_tenant.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -28,24 +29,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; set NVCC or install the CUDA toolkit")
 
 
-def _stale() -> bool:
-    if not os.path.exists(OUT):
+def _stale(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, "..", "include", "bitdelta_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
+def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> str:
+    out_path = OUT_BRINGUP if bringup else OUT
+    if not force and not _stale(out_path):
+        return out_path
     nvcc = _nvcc()
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build", "bringup" if bringup else "release")
+    extra = ["-DBD_BRINGUP"] if bringup else []
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
@@ -55,12 +58,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose or "warning" in out.lower():
             print(out, file=sys.stderr)
         objs.append(obj)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", *objs, "-o", OUT, "-ldl"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", *objs, "-o", out_path, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return OUT
+    return out_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bringup="--bringup" in sys.argv))

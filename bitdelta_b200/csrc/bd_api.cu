@@ -57,11 +57,12 @@ extern "C" BD_API int bd_abi_version(void) { return BD_ABI_VERSION; }
 extern "C" BD_API const char* bd_last_error(void) { return last_error_ref().c_str(); }
 extern "C" BD_API uint64_t bd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-// Bring-up instrumentation (not part of the reference-facing surface): device buffer of 64 x 16 int64 clock64 stamps
-// written by CTA 0 of the tcgen05 kernel; nullptr disables it.
+#ifdef BD_BRINGUP
+// Bring-up library only (libbitdelta_b200_bringup.so): device buffer of 64 x 16 int64 clock64 stamps written by CTA 0 of
+// the tcgen05 kernel (nullptr disables it) and the A/B knobs of dbg_flags() in bd_umma.cu.
 extern "C" BD_API void bd_debug_set_trace(void* device_buffer) { umma_set_trace(reinterpret_cast<long long*>(device_buffer)); }
-
 extern "C" BD_API void bd_debug_set_flags(int flags, int load_group) { umma_set_debug(flags, load_group); }
+#endif
 
 extern "C" BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n) {
   if (max_rows <= 0 || max_n <= 0) return 0;

@@ -104,7 +104,9 @@ int launch_fwd_umma(const FwdProblem& p);
 bool umma_supports(const FwdProblem& p, const char** why);
 size_t simt_workspace_bytes(int64_t rows, int64_t N);
 size_t umma_workspace_bytes(int64_t rows, int64_t N);
+#ifdef BD_BRINGUP
 void umma_set_trace(long long* buf);
 void umma_set_debug(int flags, int load_group);
+#endif
 
 }  // namespace bd

@@ -55,6 +55,9 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxRows = 128;  // rows (tokens) per launch
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 24;
+// 8-bit delta path: static exponent windows of the activation split (see xperm_job)
+constexpr int kD8Buckets = 5;
+constexpr int kD8ExpLo = 127 - 60;  // biased bf16 exponent of the lowest bucket's lower edge (2^-60)
 
 // ---------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,9 +193,20 @@ struct UmmaArgs {
   uint32_t stage_bytes, off_masks, off_x;     // stage layout: [W tile][masks][X tile]
   uint32_t off_xp, xp_buf_bytes;              // permuted activation tiles, one per A buffer
   uint32_t tx_bytes;
-  int dbg_flags;     // bring-up only: bit 0 = stream the operands but skip unpack / MMA / epilogue (pure TMA bandwidth)
+  int dbg;           // bring-up builds only (-DBD_BRINGUP): see dbg_flags() below; always 0 in the release library
   long long* trace;  // optional [64 units][16 slots] clock64 timestamps of CTA 0 (bring-up instrumentation)
 };
+
+// Bring-up knobs exist only in the -DBD_BRINGUP build (libbitdelta_b200_bringup.so, used by tools/): the release library
+// compiles them to the constant 0 and has no trace instantiation, no mutable globals and no bd_debug_* entry points.
+// bit 0 = stream the operands but skip unpack / MMA / epilogue, bit 2 = producer waits for the TMEM rendezvous,
+// bit 3 = unpack warps split tenants (not units), bit 4 = unpack without tcgen05.st, bit 5 = no MMAs (commits only),
+// bit 6 = no activation permute / split.
+#ifdef BD_BRINGUP
+__device__ __forceinline__ int dbg_flags(const UmmaArgs& a) { return a.dbg; }
+#else
+__device__ __forceinline__ constexpr int dbg_flags(const UmmaArgs&) { return 0; }
+#endif
 
 template <bool TRACE>
 __device__ __forceinline__ void trace_mark(const UmmaArgs& a, int it, int slot) {
@@ -326,7 +340,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // (measured: 24 KB per quadrant and round in ~1640 cycles), which at 6 tenants is most of the per-unit HBM time; with
   // alternating units one warp's stores drain while the other warp is in its per-unit synchronisation (release check,
   // fences, wait::st, barrier arrive, loop), instead of both warps paying that with the store port idle.
-  const bool alt_units = DELTA8 && !xperm_shared && !(a.dbg_flags & 8);
+  const bool alt_units = DELTA8 && !xperm_shared && !(dbg_flags(a) & 8);
   const int afull_threads = alt_units ? (kUnpackWarps / 2 + kXpermWarps + 1) * 32 : kAFullThreads;
 
   // Programmatic dependent launch: let the next kernel of the stream be scheduled as soon as SMs free up.  Its CTAs run
@@ -357,10 +371,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   __syncthreads();  // mbarriers initialised
   // The TMA producer needs nothing else: it starts requesting the first weight / sign stages right away, while the other
   // warps allocate tensor memory and zero the permuted-activation tiles and rendezvous without it.
-  if (warp != kWarpProducer || (a.dbg_flags & 4)) {
+  if (warp != kWarpProducer || (dbg_flags(a) & 4)) {
     if (warp == kWarpMma) tmem_alloc(&tmem_base_slot, kTmemCols);
     // zero the permuted-activation tiles once: rows >= m of every tenant tile stay zero for the whole kernel
-    const bool all = (a.dbg_flags & 4) != 0;
+    const bool all = (dbg_flags(a) & 4) != 0;
     const uint32_t part = all ? threadIdx.x : threadIdx.x - (warp > kWarpProducer ? 32u : 0u);
     const uint32_t nparts = all ? kThreads : kThreads - 32;
     for (uint32_t i = part * 16; i < a.n_abuf * a.xp_buf_bytes; i += nparts * 16)
@@ -382,19 +396,33 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // destination tiles use the 128-byte swizzle (chunk index XOR row % 8).
   auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job) {
     if constexpr (DELTA8) {
-      // 8-bit delta path.  job = (row r, 32-group g, c): one 32-bit output word per piece, holding K slots 4c..4c+3 of the
-      // group = activations k = c + 8q, q = 0..3 (the order the e4m3 sign registers are built in).  Jobs are kept this
-      // small on purpose: a warp executes a job's instructions once however many lanes are active, and the issue slots
-      // of the sub-partition this warp shares with two unpack warps are the scarce resource.
-      // Every bf16 activation is split EXACTLY into three e5m2 pieces p1 + p2 + p3 (round-to-nearest residual chain:
-      // 3 + 3 + 2 significant bits cover bf16's 8), one B-operand row per piece, so the tensor core multiplies the
-      // unrounded activation; the epilogue adds the three partial sums.
+      // 8-bit delta path (one row per tenant).  job = (row r, 32-group g, c): one 32-bit output word per B-operand row,
+      // holding K slots 4c..4c+3 of the group = activations k = c + 8q, q = 0..3 (the order the e4m3 sign registers are
+      // built in).  Jobs are kept this small on purpose: a warp executes a job's instructions once however many lanes
+      // are active, and the issue slots of the sub-partition this warp shares with two unpack warps are the scarce resource.
+      //
+      // Every bf16 activation is represented EXACTLY by three e5m2 pieces p1 + p2 + p3 (round-to-nearest residual chain:
+      // 3 + 3 + 2 significant bits cover bf16's 8) of x * 2^-c_b, where b is one of kD8Buckets static exponent windows of 24
+      // binades: e5m2 holds the three pieces exactly while the scaled exponent stays in [-9, 14] (lowest piece bit >= 2^-16,
+      // p1 <= 2^15), so bucket b takes the activations with 2^(-60+24b) <= |x| < 2^(-36+24b) and the five buckets cover
+      // [2^-60, 2^60) -- whatever the scale of the row, with no data-dependent pre-pass.  Each (bucket, piece) is its own
+      // B-operand row (15 of the tenant's 16 accumulator columns); an element is zero in the rows of the other buckets.
+      // The epilogue adds sum_b 2^c_b * (d[3b] + d[3b+1] + d[3b+2]) in fp32.  |x| < 2^-60 degrades gradually (absolute error
+      // < 2^-76 per element); |x| >= 2^60, inf and NaN become NaN pieces: the result is NaN, never a silently clipped number.
       const int r = job >> 4, g = (job >> 3) & 1, c = job & 7;
       const uint8_t* src = xsrc + r * 128 + 2 * (c & 7);
       float f[4];
+      uint32_t bsel = 0, bad = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)  // element 32g + c + 8q lives in 16-byte chunk 4g + q (swizzled by the row)
-        f[q] = F16<T16>::to_f32(*reinterpret_cast<const T16*>(src + (((4 * g + q) ^ (r & 7)) << 4)));
+      for (int q = 0; q < 4; ++q) {  // element 32g + c + 8q lives in 16-byte chunk 4g + q (swizzled by the row)
+        const uint32_t bits = *reinterpret_cast<const unsigned short*>(src + (((4 * g + q) ^ (r & 7)) << 4));
+        const int eb = (int)((bits >> 7) & 0xFFu);                      // biased exponent; bucket = floor((eb - 67) / 24)
+        const int b = min((max(eb - kD8ExpLo, 0) * 171) >> 12, kD8Buckets - 1);
+        bsel |= (uint32_t)b << (4 * q);
+        bad |= (eb >= kD8ExpLo + 24 * kD8Buckets ? 0xFFu : 0u) << (8 * q);
+        // x * 2^(51 - 24b): the bucket's lowest exponent lands on 2^-9
+        f[q] = __uint_as_float(bits << 16) * __uint_as_float((uint32_t)(127 + 51 - 24 * b) << 23);
+      }
       uint32_t pw[3];
 #pragma unroll
       for (int piece = 0; piece < 3; ++piece) {
@@ -408,13 +436,21 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           f[0] -= b01.x; f[1] -= b01.y; f[2] -= b23.x; f[3] -= b23.y;
         }
       }
-      const int t = (int)(((uint32_t)r * a.inv_m) >> 16), i = r - t * a.m;
+      pw[0] = (pw[0] & ~bad) | (0x7E7E7E7Eu & bad);  // out of range / non-finite: e5m2 NaN
+      const int t = r;                               // one row per tenant on this path
       // tenant tile: [16 rows x 64 B] as 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
       uint8_t* tile = xp + t * 1024 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
 #pragma unroll
-      for (int piece = 0; piece < 3; ++piece) {
-        const int rr = 3 * i + piece;
-        *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = pw[piece];
+      for (int b = 0; b < kD8Buckets; ++b) {
+        // byte q of the word goes to bucket b's rows iff element q is in bucket b: PRMT selector nibble q = q, else 4 (-> 0)
+        const uint32_t ne = bsel ^ (0x1111u * b);
+        const uint32_t nz = (ne | (ne >> 1) | (ne >> 2)) & 0x1111u;
+        const uint32_t sel = (0x3210u & ~(nz * 7u)) | (nz << 2);
+#pragma unroll
+        for (int piece = 0; piece < 3; ++piece) {
+          const int rr = 3 * b + piece;
+          *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = __byte_perm(pw[piece], 0, sel);
+        }
       }
       return;
     }
@@ -504,7 +540,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       st_next.advance(a.stages);
       if (leader) {
         trace_mark<TRACE>(a, u - u_begin, 6);
-        if (!(a.dbg_flags & 1)) {
+        if (!(dbg_flags(a) & (1 | 32))) {
         const uint32_t w_lo = w_lo0 + st.idx * stage_lo;
         const uint32_t x_lo = w_lo + x_off_lo;
         const uint32_t xp_lo = xp_lo0 + ab.idx * xp_buf_lo;
@@ -554,7 +590,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
       wait_released(&s_released, u - u_begin);
-      if (!NATK && !(a.dbg_flags & 1)) {
+      if (!NATK && !(dbg_flags(a) & (1 | 64))) {
         const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
         uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
         // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
@@ -624,7 +660,11 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
                 // r = (~sh & 0x80808080) | 0x38383838 : four e4m3 values, +1.0 = 0x38, -1.0 = 0xB8 (one LOP3, LUT 0xAE)
                 asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[c]) : "r"(sh), "r"(sign_mask), "r"(kOne));
               }
-              tmem_st8(ta + t * 16 + jj * 8, r);
+              if (dbg_flags(a) & 16) {
+                asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+              } else {
+                tmem_st8(ta + t * 16 + jj * 8, r);
+              }
             } else {
               uint32_t r[16];
 #pragma unroll
@@ -667,7 +707,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           if (tr) trace_mark<TRACE>(a, it, 1);
           Ring st_i = st, ab_i = ab;
           if (my) { st_i.advance(a.stages); ab_i.advance(a.n_abuf); }
-          if (!(a.dbg_flags & 1)) {
+          if (!(dbg_flags(a) & 1)) {
             unpack_unit(smem + (size_t)st_i.idx * a.stage_bytes, ab_i.idx, 0, 1);
             if (tr) trace_mark<TRACE>(a, it, 3);
             tc_wait_st();
@@ -683,7 +723,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       tc_fence_after();
       if (tr) trace_mark<TRACE>(a, it, 1);
       Ring st_i = st, ab_i = ab;
-      if (!(a.dbg_flags & 1)) {
+      if (!(dbg_flags(a) & 1)) {
         for (int i = 0; i < g; ++i) {
           const uint8_t* sp = smem + (size_t)st_i.idx * a.stage_bytes;
           if (!NATK && xperm_shared) {  // large row counts: the unpack warps share the activation permutation
@@ -708,9 +748,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       }
       if (tr) trace_mark<TRACE>(a, it, 11);
       }
+      if (tr) trace_mark<TRACE>(a, it, 12);
       u += g;
       kb += g - 1;  // kb = K block of the last unit of the round (the epilogue below looks at it)
-      if ((a.dbg_flags & 1) && seg_last) {
+      if ((dbg_flags(a) & 1) && seg_last) {
         mbar_wait(&bar_dfull, dphase);
         dphase ^= 1u;
         if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
@@ -742,31 +783,26 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
 
         if constexpr (DELTA8) {
-          // delta accumulator: 16 columns per tenant, column 3i+p = piece p of row i (m <= 5); the two warps of a
-          // quadrant take alternate tenants
+          // delta accumulator: 16 columns per tenant (one row per tenant), column 3b+p = piece p of exponent bucket b,
+          // scaled by 2^(51-24b); the two warps of a quadrant take alternate tenants
           for (int t = grp; t < a.T; t += 2) {
             const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
-            float d0[8], d1[8], bv[5];
+            float d0[8], d1[8], bv = 0.f;
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16, d0);
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16 + 8, d1);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              bv[i] = 0.f;
-              if (HAS_BASE && i < a.m) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + i);
-            }
+            if (HAS_BASE) bv = tmem_ld1(tmem_base + lane_addr + col_dbase + t);
             tc_wait_ld();
-            const float dsum[5] = {d0[0] + d0[1] + d0[2], d0[3] + d0[4] + d0[5], d0[6] + d0[7] + d1[0], d1[1] + d1[2] + d1[3],
-                                   d1[4] + d1[5] + d1[6]};
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              if (i >= a.m) continue;
-              const int r = t * a.m + i;
-              const float v = HAS_BASE ? fmaf(cf, dsum[i], bv[i]) : dsum[i];
-              if (full_k) {
-                if (n < seg_n) y[(int64_t)r * seg_n + n] = F16<T16>::from_f32(v);
-              } else {
-                part[(size_t)r * kTileN + row] = v;
-              }
+            // small buckets first; each term is exact in fp32 up to the accumulator's own rounding
+            float dsum = (d0[0] + d0[1] + d0[2]) * 0x1p-51f;
+            dsum = fmaf(d0[3] + d0[4] + d0[5], 0x1p-27f, dsum);
+            dsum = fmaf(d0[6] + d0[7] + d1[0], 0x1p-3f, dsum);
+            dsum = fmaf(d1[1] + d1[2] + d1[3], 0x1p21f, dsum);
+            dsum = fmaf(d1[4] + d1[5] + d1[6], 0x1p45f, dsum);
+            const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
+            if (full_k) {
+              if (n < seg_n) y[(int64_t)t * seg_n + n] = F16<T16>::from_f32(v);
+            } else {
+              part[(size_t)t * kTileN + row] = v;
             }
           }
         } else
@@ -854,6 +890,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       }
       if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
       if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
+      if (tr) trace_mark<TRACE>(a, it, 13);
     }
   }
 
@@ -885,8 +922,13 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+#ifdef BD_BRINGUP
 long long* g_trace_buf = nullptr;
-int g_dbg_flags = 0;  // bit 0 = stream only, bit 1 = force the 16-bit delta path, bit 2 = producer waits for the TMEM rendezvous, bit 3 = unpack warps split tenants (not units)
+int g_dbg_flags = 0;  // device bits: see dbg_flags(); host bit 1 = force the 16-bit delta path
+#else
+constexpr long long* g_trace_buf = nullptr;
+constexpr int g_dbg_flags = 0;
+#endif
 
 struct DeviceInfo {
   int sms = 0, smem_optin = 0, cc_major = 0;
@@ -916,14 +958,14 @@ struct UmmaPlan {
 UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bool d8) {
   UmmaPlan p;
   p.d8 = d8;
-  if (d8 && m > 5) { p.why = "the 8-bit delta path takes at most 5 rows per tenant"; return p; }
+  if (d8 && m != 1) { p.why = "the 8-bit delta path takes one row per tenant"; return p; }
   const int64_t rows = T * m;
   if (rows > kMaxRows) { p.why = "more than 128 rows per launch"; return p; }
   if (T > 1 && m > 16) { p.why = "multi-tenant launches support at most 16 rows per tenant"; return p; }
   if (N % 4 != 0) { p.why = "N must be a multiple of 4 (TMA row pitch of the sign words)"; return p; }
   if (K % 32 != 0) { p.why = "K must be a multiple of 32"; return p; }
   if ((N + kTileN - 1) / kTileN > (int64_t)(kWsCounterBytes / sizeof(unsigned))) { p.why = "too many N tiles"; return p; }
-  p.mp = d8 ? 16 : (int)((m + 15) / 16 * 16);  // delta accumulator columns per tenant (8-bit path: 3 pieces per row)
+  p.mp = d8 ? 16 : (int)((m + 15) / 16 * 16);  // delta accumulator columns per tenant (8-bit path: 5 buckets x 3 pieces of the one row)
   p.a_cols_tenant = d8 ? kBlockK / 4 : kBlockK / 2;
   p.ntb = (int)((rows + 15) / 16 * 16);
   const int64_t a_cols_one = T * p.a_cols_tenant;
@@ -955,11 +997,10 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
   return p;
 }
 
-extern int g_dbg_flags;
 // Picks the 8-bit delta path (e4m3 signs x e5m2 activation pieces: half the TMEM traffic, half the unpack work, half the
-// MMAs) whenever it applies -- bf16 activations, at most 5 rows per tenant -- else the 16-bit path.
+// MMAs) whenever it applies -- bf16 activations, one row per tenant (decode) -- else the 16-bit path.
 UmmaPlan choose_plan(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, bool has_base) {
-  if (dtype == BD_BF16 && m <= 5 && !(g_dbg_flags & 2)) {
+  if (dtype == BD_BF16 && m == 1 && !(g_dbg_flags & 2)) {
     UmmaPlan p8 = plan_umma(T, m, K, N, has_base, true);
     if (p8.ok) return p8;
   }
@@ -1113,7 +1154,7 @@ static int launch_one(const FwdProblem& p) {
   a.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p.workspace) + kWsUmmaCounterOffset);
   a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + kWsScratchOffset);
   a.trace = g_trace_buf;
-  a.dbg_flags = g_dbg_flags;
+  a.dbg = g_dbg_flags;
 
   const CUtensorMapDataType dt16 = p.dtype == BD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   alignas(64) UmmaMaps maps{};
@@ -1137,7 +1178,9 @@ static int launch_one(const FwdProblem& p) {
   }
   if (p.dtype == BD_BF16) {
     if (plan.d8) {
-      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, false, true>(p, plan, maps, a, grid);  // instrumented build
+#ifdef BD_BRINGUP
+      if (has_base && a.trace) return launch_typed<__nv_bfloat16, true, true, false, true>(p, plan, maps, a, grid);  // instrumented variant
+#endif
       return has_base ? launch_typed<__nv_bfloat16, true, true, false, false>(p, plan, maps, a, grid)
                       : launch_typed<__nv_bfloat16, false, true, false, false>(p, plan, maps, a, grid);
     }
@@ -1154,8 +1197,10 @@ static int launch_one(const FwdProblem& p) {
                   : launch_typed<__half, false, false, false, false>(p, plan, maps, a, grid);
 }
 
+#ifdef BD_BRINGUP
 void umma_set_trace(long long* buf) { g_trace_buf = buf; }
 void umma_set_debug(int flags, int) { g_dbg_flags = flags; }
+#endif
 
 // Decomposes a problem into launches the kernel takes: tenant groups that fit the TMEM budget, then 128-row chunks of a
 // single tenant.  Sub-launches are stream-ordered and share the workspace (each leaves its counters at zero).

@@ -143,12 +143,15 @@ BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n);
 /* Which kernel BD_KERNEL_AUTO would pick for this problem (BD_KERNEL_SIMT or BD_KERNEL_UMMA). */
 BD_API int bd_select_kernel(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, int has_base);
 
-/* Bring-up instrumentation: device buffer of 64 x 16 int64 clock64 stamps written by CTA 0 of the tcgen05 kernel
- * (per work unit: barrier waits, unpack, MMA issue); NULL disables it.  Not used by the Python surface. */
-BD_API void bd_debug_set_trace(void* device_buffer);
-/* Bring-up knobs of the tcgen05 kernel: flags bit 0 = stream operands only (no unpack/MMA/epilogue, outputs undefined),
- * bit 1 = force the 16-bit delta path; the second argument is reserved. */
-BD_API void bd_debug_set_flags(int flags, int load_group);
+/* Bring-up instrumentation is NOT part of this library: the per-unit clock64 trace and the A/B knobs of the tcgen05 kernel
+ * exist only in libbitdelta_b200_bringup.so (python bitdelta_b200/build.py --bringup, compiled with -DBD_BRINGUP), which
+ * tools/umma_trace.py and tools/kernel_bench.py load explicitly.  The release library has no mutable global state besides
+ * mutex-guarded caches. */
+#ifdef BD_BRINGUP
+#define BD_BRINGUP_API BD_API
+BD_BRINGUP_API void bd_debug_set_trace(void* device_buffer); /* 64 x 16 int64 stamps of CTA 0; NULL disables */
+BD_BRINGUP_API void bd_debug_set_flags(int flags, int reserved);
+#endif
 
 #ifdef __cplusplus
 }

@@ -726,3 +726,95 @@ def test_cuda_graph_capture_of_the_fused_forward():
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(y_graph, y_eager)
+
+
+# ------------------------------------------------------------------------------------------------ activation range
+# The decode launches of the tcgen05 kernel (bf16, one row per tenant) feed the delta product from 8-bit operands: the
+# activations are split exactly into e5m2 pieces inside static exponent buckets (bd_umma.cu, xperm_job).  These cases
+# leave the randn scale every other test uses: the result must stay inside the SAME tolerance whatever the magnitude of
+# the row, like the reference, which accumulates the unrounded activation (binary_gemm_kernel.py:260-278).
+SCALES = [1e-12, 1e-6, 1e-4, 1e-3, 1.0, 1e3, 6e4, 1e9]
+
+
+def _tenant_problem(T, m, K, N, seed):
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.003 + 0.0005).bfloat16()
+    x = torch.randn(T, m, K, generator=gen, device=DEV)
+    return gen, w, masks, coeffs, x
+
+
+@pytest.mark.parametrize("kernel", ["umma", "simt"])
+@pytest.mark.parametrize("m", [1, 3])
+@pytest.mark.parametrize("scale", SCALES)
+def test_activation_scale_does_not_change_the_error(kernel, m, scale):
+    T, K, N = 6, 4096, 1024
+    _, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 7 + m)
+    x = (x * scale).bfloat16()
+    signs = bd.unpack(masks).double() * 2 - 1
+    # delta only (binary_bmm): nothing hides an error of the sign product
+    c = bd.binary_bmm(x, masks, kernel=kernel)
+    exact_d = torch.bmm(x.double(), signs)
+    assert_close_to_exact(c, exact_d.cpu().numpy(), f"binary_bmm scale {scale:g}")
+    # DiffCompressModule, with a coefficient large enough for the delta term to matter (0.5 .. 1.5)
+    big = (coeffs.float() * 500).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    for cf in (coeffs, big):
+        mod = bd.DiffCompressModule(lin, masks, cf)
+        mod.kernel = kernel
+        y = mod(x)
+        exact = x.double() @ w.double().T + cf.double()[:, None, None] * exact_d
+        assert_close_to_exact(y, exact.cpu().numpy(), f"DiffCompressModule scale {scale:g}")
+
+
+@pytest.mark.parametrize("kernel", ["umma", "simt"])
+def test_wide_dynamic_range_rows(kernel):
+    # every row mixes magnitudes from 1e-9 to 1e9 (exponents drawn uniformly) plus a few massive outlier channels
+    T, m, K, N = 6, 1, 4096, 512
+    gen, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 11)
+    expo = torch.rand(T, m, K, generator=gen, device=DEV) * 18 - 9
+    x = (x * torch.pow(10.0, expo))
+    x[:, :, ::251] *= 1e4
+    x = x.bfloat16()
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact_d = torch.bmm(x.double(), signs)
+    c = bd.binary_bmm(x, masks, kernel=kernel)
+    assert_close_to_exact(c, exact_d.cpu().numpy(), "binary_bmm wide rows")
+    # ... and rows whose elements differ by tenant: tenant t lives around 10^(4t - 10)
+    x2 = (torch.randn(T, m, K, generator=gen, device=DEV) * torch.pow(10.0, 4.0 * torch.arange(T, device=DEV) - 10.0)[:, None, None]).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, (coeffs.float() * 300).bfloat16())
+    mod.kernel = kernel
+    y = mod(x2)
+    exact = x2.double() @ w.double().T + mod.coeff.double()[:, None, None] * torch.bmm(x2.double(), signs)
+    got = y.double()
+    for t in range(T):  # per tenant: the tolerance's absolute floor must not be set by the largest tenant
+        assert_close_to_exact(y[t], exact[t].cpu().numpy(), f"tenant {t}")
+    assert torch.isfinite(got).all()
+
+
+def test_non_finite_and_out_of_range_activations_are_not_clipped():
+    # inf / NaN / |x| >= 2^60 in one tenant's row: that tenant's outputs are non-finite (never a silently saturated
+    # number), the other tenants are unaffected
+    T, m, K, N = 6, 1, 1024, 256
+    _, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 13)
+    x = x.bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    mod.kernel = "umma"
+    y_ref = mod(x).clone()
+    for t, bad in ((1, float("inf")), (3, float("nan")), (4, 2.0**70)):
+        xb = x.clone()
+        xb[t, 0, 517] = bad
+        for y in (mod(xb), bd.binary_bmm(xb, masks, kernel="umma")):
+            assert not torch.isfinite(y[t]).any(), f"tenant {t} with {bad}"
+            others = [i for i in range(T) if i != t]
+            assert torch.isfinite(y[others]).all()
+        assert torch.equal(mod(xb)[others], y_ref[others])

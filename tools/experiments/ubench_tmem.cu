@@ -57,6 +57,85 @@ __device__ __forceinline__ void tmem_st<32>(uint32_t taddr, uint32_t v) {
       : "memory");
 }
 
+
+// tcgen05.st of NREG copies of one register, any shape:  ST(shape, xN, NREG)
+#define R1 "%1"
+#define R2 R1 ", " R1
+#define R4 R2 ", " R2
+#define R8 R4 ", " R4
+#define R16 R8 ", " R8
+#define R32 R16 ", " R16
+#define R64 R32 ", " R32
+#define DEF_ST(NAME, SHAPE, XN, REGS)                                                                                      \
+  struct NAME {                                                                                                            \
+    static constexpr int kBytes = 0;                                                                                       \
+    static __device__ __forceinline__ void st(uint32_t taddr, uint32_t v) {                                                \
+      asm volatile("tcgen05.st.sync.aligned." SHAPE "." XN ".b32 [%0], {" REGS "};" ::"r"(taddr), "r"(v) : "memory");      \
+    }                                                                                                                      \
+  };
+DEF_ST(St32x32_x1, "32x32b", "x1", R1)
+DEF_ST(St32x32_x4, "32x32b", "x4", R4)
+DEF_ST(St32x32_x8, "32x32b", "x8", R8)
+DEF_ST(St32x32_x16, "32x32b", "x16", R16)
+DEF_ST(St32x32_x32, "32x32b", "x32", R32)
+DEF_ST(St32x32_x64, "32x32b", "x64", R64)
+DEF_ST(St16x256_x1, "16x256b", "x1", R4)
+DEF_ST(St16x256_x2, "16x256b", "x2", R8)
+DEF_ST(St16x256_x4, "16x256b", "x4", R16)
+DEF_ST(St16x256_x8, "16x256b", "x8", R32)
+DEF_ST(St16x128_x2, "16x128b", "x2", R4)
+DEF_ST(St16x128_x8, "16x128b", "x8", R16)
+DEF_ST(St16x64_x4, "16x64b", "x4", R4)
+DEF_ST(St16x64_x16, "16x64b", "x16", R16)
+
+// Generic store-throughput kernel: each of `warps` warps issues `n_inst` stores of type S per pass (columns advance by
+// `col_step`, wrapping inside the warp's 256-column half), `iters` passes.  bytes are computed on the host from REGS.
+template <typename S>
+__global__ void __launch_bounds__(512) stg_kernel(int warps, int iters, int n_inst, int col_step, long long* out) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + ((warp >> 2) & 1) * 256;
+  long long t0 = 0, t1 = 0;
+  if (warp < warps) {
+    S::st(base, lane);
+    tc_wait_st();
+    __syncwarp();
+    t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+      for (int i = 0; i < n_inst; ++i) S::st(base + ((i * col_step) & 255), lane + it);
+    }
+    tc_wait_st();
+    t1 = clock64();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (lane == 0 && warp < warps && blockIdx.x == 0) out[warp] = t1 - t0;
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 512);
+  }
+}
+template <typename S>
+void run_stg(const char* name, int regs, int col_step, int warps, long long* d_out) {
+  const int iters = 64, n_inst = 32;
+  CK(cudaMemset(d_out, 0, 16 * sizeof(long long)));
+  stg_kernel<S><<<148, 512>>>(warps, iters, n_inst, col_step, d_out);
+  CK(cudaDeviceSynchronize());
+  long long h[16];
+  CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  const double bytes_per_warp = (double)iters * n_inst * regs * 32 * 4;
+  long long worst = 0;
+  for (int w = 0; w < warps; ++w) worst = h[w] > worst ? h[w] : worst;
+  std::printf("st %-12s regs=%-3d warps=%-2d: %8lld cyc  %6.1f cyc/inst/warp  %6.1f B/clk/warp  %7.1f B/clk/SM\n", name, regs, warps, worst,
+              (double)worst / (iters * n_inst), bytes_per_warp / worst, bytes_per_warp * warps / worst);
+}
+
 // ---------------------------------------------------------------------------------------------------- 1. store throughput
 // `warps` warps (1..8); warp w stores into lane quadrant w % 4, columns [(w / 4) * 256, +256) in steps of X, `iters` passes.
 template <int X>
@@ -198,13 +277,232 @@ __global__ void __launch_bounds__(192) mma_kernel(int n_mma, int store_warps, lo
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------- 3. other issue loops
+// MODE 1: SS kind::f8f6f4 (A = 128 x 32 B no-swizzle tile in shared memory), N = 16
+// MODE 2: SS kind::f16 bf16 (A = 128 x 64 bf16 SWIZZLE_128B tile, K = 16 per MMA), N = 16   (the base product)
+// MODE 3: tcgen05.cp 128x256b (shared memory -> 128 lanes x 8 columns = 4 KB per instruction)
+// MODE 4: TS kind::f8f6f4 with N = 8
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+template <int MODE>
+__global__ void __launch_bounds__(192) issue_kernel(int n_op, int store_warps, long long* out, int n_acc = 2) {
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t bar;
+  __shared__ volatile int stop;
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  uint8_t* tiles = dsm + ((1024u - (smem_u32(dsm) & 1023u)) & 1023u);  // [0,16K) A tile, [16K, 18K) B tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 18 * 1024; i += blockDim.x) tiles[i] = 0x38;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stop = 0;
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  if (warp < 4) {
+    tmem_st<16>(tb + ((uint32_t)(warp * 32) << 16) + 64, 0x38383838u);
+    tc_wait_st();
+    tc_fence_before();
+    asm volatile("bar.sync 1, 160;" ::: "memory");
+    if (warp < store_warps) {
+      uint32_t spins = 0;
+      while (!stop && ++spins < (1u << 20)) {
+#pragma unroll
+        for (int c = 0; c < 256; c += 8) tmem_st<8>(tb + ((uint32_t)(warp * 32) << 16) + 256 + c, lane);
+      }
+      tc_wait_st();
+    }
+  } else if (warp == 4) {
+    asm volatile("bar.sync 1, 160;" ::: "memory");
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t a_lo = (smem_u32(tiles) & 0x3FFFFu) >> 4, b_lo = (smem_u32(tiles + 16384) & 0x3FFFFu) >> 4;
+      const uint32_t idesc8_16 = make_idesc8(16), idesc8_8 = make_idesc8(8);
+      const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+      const long long t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < n_op; ++i) {
+        const uint32_t acc = i > 1;
+        if (MODE == 1) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+              "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+              "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t}"
+              ::"r"(tb + (i & 1) * 16), "r"((a_lo + (i & 3) * 2) | kDesc8LoLbo), "r"(b_lo | kDesc8LoLbo), "r"(kDesc8Hi), "r"(idesc8_16), "r"(acc)
+              : "memory");
+        } else if (MODE == 2) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+              "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+              ::"r"(tb + (i & 1) * 16), "r"(a_lo + (i & 3) * 2), "r"(b_lo + (i & 3) * 2), "r"(kDescHiSw128), "r"(idesc16), "r"(acc)
+              : "memory");
+        } else if (MODE == 3) {
+          asm volatile(
+              "{\n\t.reg .b64 da;\n\tmov.b64 da, {%1, %2};\n\t"
+              "tcgen05.cp.cta_group::1.128x256b [%0], da;\n\t}"
+              ::"r"(tb + 128 + (i & 15) * 8), "r"((a_lo + (i & 3) * 2) | kDesc8LoLbo), "r"(kDesc8Hi)
+              : "memory");
+        } else if (MODE == 4) {
+          mma_ts8(tb + (i & 1) * 16, tb + 64, b_lo, idesc8_8, acc);
+        } else if (MODE == 5) {  // n_acc independent accumulators (columns 128 + 16 j), N = 16
+          mma_ts8(tb + 128 + (i % n_acc) * 16, tb + 64, b_lo, idesc8_16, i >= n_acc);
+        } else if (MODE == 6) {  // latency: one MMA, commit, wait for the mbarrier -- n_op times
+          mma_ts8(tb + 128, tb + 64, b_lo, idesc8_16, acc);
+          tc_commit(&bar);
+          uint32_t spins = 0;
+          while (!mbar_try_wait(&bar, i & 1)) {
+            if (++spins > (1u << 24)) __trap();
+          }
+        } else if (MODE == 7) {  // 16 independent MMAs + commit + wait per round (one 'unit' of the decode kernel)
+          for (int j = 0; j < 16; ++j) mma_ts8(tb + 128 + (j % n_acc) * 16, tb + 64, b_lo, idesc8_16, 1);
+          tc_commit(&bar);
+          uint32_t spins = 0;
+          while (!mbar_try_wait(&bar, i & 1)) {
+            if (++spins > (1u << 24)) __trap();
+          }
+        }
+      }
+      const long long t1 = clock64();
+      if (MODE != 6 && MODE != 7) {
+      tc_commit(&bar);
+      uint32_t spins = 0;
+      while (!mbar_try_wait(&bar, 0)) {
+        if (++spins > (1u << 24)) __trap();
+      }
+      }
+      const long long t2 = clock64();
+      if (blockIdx.x == 0) {
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+      }
+      stop = 1;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tb, 512);
+  }
+}
+template <int MODE>
+void run_issue(const char* what, int store_warps, long long* d_out, int n_acc = 2) {
+  const int n = 512;
+  CK(cudaFuncSetAttribute(issue_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 1024));
+  CK(cudaMemset(d_out, 0, 16 * sizeof(long long)));
+  issue_kernel<MODE><<<148, 192, 20 * 1024>>>(n, store_warps, d_out, n_acc);
+  CK(cudaDeviceSynchronize());
+  long long h[2];
+  CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  std::printf("%-44s %d op, %d storing warp(s): issue %.1f cyc/op, issue+complete %.1f cyc/op\n", what, n, store_warps, (double)h[0] / n,
+              (double)h[1] / n);
+}
+
+// ---------------------------------------------------------------------------------------------------- 4. concurrent issuers
+// `issuers` warps (1..4) each issue n_op TS MMAs (N = ncols) into their own accumulator; elect.sync leader, uniform loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__global__ void __launch_bounds__(256) multi_issue_kernel(int n_op, int issuers, int ncols, long long* out) {
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t bar[4];
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  uint8_t* tiles = dsm + ((1024u - (smem_u32(dsm) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 18 * 1024; i += blockDim.x) tiles[i] = 0x38;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  if (warp < 4) {
+    tmem_st<16>(tb + ((uint32_t)(warp * 32) << 16) + 480, 0x38383838u);  // A operand columns [480, 496)
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp >= 4 && warp < 4 + issuers) {
+    const int w = warp - 4;
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc8(ncols);
+    const uint32_t b_lo = (smem_u32(tiles + 16384) & 0x3FFFFu) >> 4;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (leader) {
+      t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < n_op; i += 4) {
+        mma_ts8(tb + w * 112, tb + 480, b_lo, idesc, 1);
+        mma_ts8(tb + w * 112, tb + 480, b_lo, idesc, 1);
+        mma_ts8(tb + w * 112, tb + 480, b_lo, idesc, 1);
+        mma_ts8(tb + w * 112, tb + 480, b_lo, idesc, 1);
+      }
+      t1 = clock64();
+      tc_commit(&bar[w]);
+      uint32_t spins = 0;
+      while (!mbar_try_wait(&bar[w], 0)) {
+        if (++spins > (1u << 24)) __trap();
+      }
+      t2 = clock64();
+      if (blockIdx.x == 0) {
+        out[2 * w] = t1 - t0;
+        out[2 * w + 1] = t2 - t0;
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tb, 512);
+  }
+}
+void run_multi(int issuers, int ncols, long long* d_out) {
+  const int n = 512;
+  CK(cudaFuncSetAttribute(multi_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 1024));
+  CK(cudaMemset(d_out, 0, 16 * sizeof(long long)));
+  multi_issue_kernel<<<148, 256, 20 * 1024>>>(n, issuers, ncols, d_out);
+  CK(cudaDeviceSynchronize());
+  long long h[8];
+  CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  std::printf("elect-issued TS f8f6f4 N=%-3d, %d issuer warp(s), %d MMAs each:", ncols, issuers, n);
+  for (int w = 0; w < issuers; ++w) std::printf("  [w%d issue %.1f, complete %.1f cyc/MMA]", w, (double)h[2 * w] / n, (double)h[2 * w + 1] / n);
+  std::printf("\n");
+}
+
 int main() {
   long long* d_out;
-  CK(cudaMalloc(&d_out, 8 * sizeof(long long)));
-  for (int warps : {1, 4, 8}) {
-    run_st<8>(warps, d_out);
-    run_st<16>(warps, d_out);
-    run_st<32>(warps, d_out);
+  CK(cudaMalloc(&d_out, 16 * sizeof(long long)));
+  for (int warps : {1, 4, 8, 16}) {
+    run_stg<St32x32_x1>("32x32b.x1", 1, 1, warps, d_out);
+    run_stg<St32x32_x4>("32x32b.x4", 4, 4, warps, d_out);
+    run_stg<St32x32_x8>("32x32b.x8", 8, 8, warps, d_out);
+    run_stg<St32x32_x16>("32x32b.x16", 16, 16, warps, d_out);
+    run_stg<St32x32_x32>("32x32b.x32", 32, 32, warps, d_out);
+    run_stg<St32x32_x64>("32x32b.x64", 64, 64, warps, d_out);
+    run_stg<St16x256_x1>("16x256b.x1", 4, 8, warps, d_out);
+    run_stg<St16x256_x2>("16x256b.x2", 8, 16, warps, d_out);
+    run_stg<St16x256_x4>("16x256b.x4", 16, 32, warps, d_out);
+    run_stg<St16x256_x8>("16x256b.x8", 32, 64, warps, d_out);
+    run_stg<St16x128_x2>("16x128b.x2", 4, 8, warps, d_out);
+    run_stg<St16x128_x8>("16x128b.x8", 16, 32, warps, d_out);
+    run_stg<St16x64_x4>("16x64b.x4", 4, 8, warps, d_out);
+    run_stg<St16x64_x16>("16x64b.x16", 16, 32, warps, d_out);
   }
   for (int store_warps : {0, 4}) {
     const int n = 512;
@@ -215,6 +513,20 @@ int main() {
     CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
     std::printf("tcgen05.mma f8f6f4 TS M=128 N=16 K=32, %d back-to-back, %d storing warp(s): issue %.1f cycles/MMA, issue+complete %.1f cycles/MMA\n", n,
                 store_warps, (double)h[0] / n, (double)h[1] / n);
+    run_issue<1>("mma f8f6f4 SS (A smem 4KB) M=128 N=16 K=32", store_warps, d_out);
+    run_issue<2>("mma f16 bf16 SS sw128 M=128 N=16 K=16", store_warps, d_out);
+    run_issue<3>("tcgen05.cp 128x256b (4 KB)", store_warps, d_out);
+    run_issue<4>("mma f8f6f4 TS M=128 N=8 K=32", store_warps, d_out);
+    for (int n_acc : {1, 2, 4, 8, 16}) {
+      char nm[64];
+      std::snprintf(nm, sizeof(nm), "mma f8f6f4 TS N=16, %d accumulators", n_acc);
+      run_issue<5>(nm, store_warps, d_out, n_acc);
+    }
+    run_issue<6>("1 MMA + commit + mbarrier wait (latency)", store_warps, d_out);
+    run_issue<7>("16 MMA (8 acc) + commit + wait, per round", store_warps, d_out, 8);
+  }
+  for (int ncols : {8, 16, 32, 96}) {
+    for (int issuers : {1, 2, 4}) run_multi(issuers, ncols, d_out);
   }
   CK(cudaFree(d_out));
   return 0;

@@ -4,6 +4,7 @@ operand sets larger than L2, so the number is device time per launch without Pyt
 usage: kernel_bench.py [kernel] [T,m,K,N ...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("BD_BRINGUP_LIB", "1")  # the library with the trace and the A/B knobs (build.py --bringup)
 import torch
 import bitdelta_b200 as bd
 from bitdelta_b200.diff import _fused_forward

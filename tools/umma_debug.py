@@ -2,6 +2,7 @@
 """Bring-up aid: compares the tcgen05 kernel with the SIMT kernel and an fp64 torch reference on a list of shapes."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("BD_BRINGUP_LIB", "1")  # the library with the trace and the A/B knobs (build.py --bringup)
 import torch
 import bitdelta_b200 as bd
 from bitdelta_b200.diff import _fused_forward
