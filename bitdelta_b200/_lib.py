@@ -94,10 +94,13 @@ def dtype_code(dt: torch.dtype) -> int:
         raise TypeError(f"bitdelta_b200 supports bfloat16/float16 activations, got {dt}") from None
 
 
-def kernel_code(name) -> int:
-    if isinstance(name, int):
-        return name
-    return _KERNELS[name]
+FLAG_STATIC_OPERANDS, FLAG_FP32_OUT = 1 << 8, 1 << 9  # bd_launch_flag
+
+
+def kernel_code(name, static_operands: bool = False, fp32_out: bool = False) -> int:
+    """`kernel` argument of the forward entry points: bd_kernel selector | bd_launch_flag bits."""
+    code = name if isinstance(name, int) else _KERNELS[name]
+    return code | (FLAG_STATIC_OPERANDS if static_operands else 0) | (FLAG_FP32_OUT if fp32_out else 0)
 
 
 def stream_ptr(device: torch.device) -> int:
@@ -111,18 +114,23 @@ def launch_count() -> int:
 # ---- per-(device, stream) zero-initialised workspaces; the kernels leave them zeroed ----
 _ws_lock = threading.Lock()
 _workspaces: dict = {}
+_WS_MAX_ROWS = 1 << 20  # bd_workspace_bytes clamps the row count to the kernels' per-launch maximum
 
 
 def workspace(device: torch.device, rows: int, n: int) -> torch.Tensor:
-    need = int(lib.bd_workspace_bytes(rows, n))
+    """The workspace of (device, current stream).  bd_workspace_bytes is bounded (row chunks are capped at 128 rows, N does
+    not enter), so the maximum is allocated once and the buffer is NEVER replaced: a CUDA graph captured earlier keeps a
+    valid pointer whatever is launched on the stream afterwards (a later, larger eager call used to free the buffer a
+    captured graph still wrote its split-K partials and tile counters to)."""
+    del rows, n  # every problem size fits the one buffer
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
     with _ws_lock:
         ws = _workspaces.get(key)
-        if ws is None or ws.numel() < need:
+        if ws is None:
             if torch.cuda.is_current_stream_capturing():
                 raise BitDeltaLibraryError(
-                    "workspace would have to grow during CUDA graph capture; run one warm-up call before capturing"
+                    "the first call on a stream allocates its workspace; run one warm-up call before capturing a CUDA graph"
                 )
-            ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+            ws = torch.zeros(int(lib.bd_workspace_bytes(_WS_MAX_ROWS, 1)), dtype=torch.uint8, device=device)
             _workspaces[key] = ws
     return ws

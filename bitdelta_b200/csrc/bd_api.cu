@@ -35,8 +35,19 @@ static int validate(const FwdProblem& p, const char* who) {
   return BD_OK;
 }
 
-static int dispatch(const FwdProblem& p, int kernel, const char* who) {
-  int rc = validate(p, who);
+// `kernel` argument of the entry points = bd_kernel selector in the low byte + bd_launch_flag bits
+static int apply_flags(FwdProblem& p, int kernel, const char* who) {
+  if (kernel & ~(0xFF | BD_FLAG_STATIC_OPERANDS | BD_FLAG_FP32_OUT)) return fail(BD_ERR_INVALID, "%s: unknown launch flags 0x%x", who, kernel & ~0xFF);
+  p.static_operands = (kernel & BD_FLAG_STATIC_OPERANDS) != 0;
+  p.fp32_out = (kernel & BD_FLAG_FP32_OUT) != 0;
+  return BD_OK;
+}
+
+static int dispatch(FwdProblem& p, int kernel, const char* who) {
+  int rc = apply_flags(p, kernel, who);
+  if (rc) return rc;
+  kernel &= 0xFF;
+  rc = validate(p, who);
   if (rc) return rc;
   const char* why = "";
   switch (kernel) {
@@ -103,9 +114,12 @@ extern "C" BD_API int bd_binarydiff_fwd_grouped(const void* x, int nseg, const v
     p.x = x; p.w = w[sg]; p.masks = masks[sg]; p.coeff = coeff[sg]; p.coeff_dtype = coeff_dtype; p.y = y[sg]; p.dtype = dtype;
     p.T = T; p.m = m; p.K = K; p.N = N[sg]; p.mask_tenant_stride = mask_tenant_stride[sg];
     p.workspace = workspace; p.workspace_bytes = workspace_bytes; p.stream = (cudaStream_t)stream;
-    int rc = validate(p, "bd_binarydiff_fwd_grouped");
+    int rc = apply_flags(p, kernel, "bd_binarydiff_fwd_grouped");
+    if (rc) return rc;
+    rc = validate(p, "bd_binarydiff_fwd_grouped");
     if (rc) return rc;
   }
+  kernel &= 0xFF;
   const char* why = "";
   bool umma_ok = kernel != BD_KERNEL_SIMT;
   for (int sg = 0; sg < nseg && umma_ok; ++sg) umma_ok = umma_supports(segs[sg], &why);

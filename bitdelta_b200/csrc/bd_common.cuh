@@ -83,6 +83,8 @@ struct FwdProblem {
   void* workspace;
   size_t workspace_bytes;
   cudaStream_t stream;
+  bool static_operands = false;  // BD_FLAG_STATIC_OPERANDS: w / sign words may be prefetched ahead of the stream's preceding kernel
+  bool fp32_out = false;         // BD_FLAG_FP32_OUT: y is fp32 (tensor-parallel partial sums)
   // Grouped launch (optional): `nseg` > 1 matrices that share x, K, T, m -- e.g. q/k/v or gate/up.  Segment 0 is the
   // main w/masks/coeff/y/N above; segments 1.. are listed here.  Every N but the last must be a multiple of 128.
   int nseg = 1;

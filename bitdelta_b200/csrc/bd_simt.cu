@@ -31,6 +31,7 @@ struct SimtArgs {
   unsigned* counters;  // [row_chunks * n_tiles]
   int64_t rows, m, K, N, mask_tenant_stride;
   int splits, slabs_per_split;
+  int fp32_out;  // BD_FLAG_FP32_OUT: y is fp32 (no rounding)
 };
 
 template <typename T, bool HAS_BASE>
@@ -162,9 +163,10 @@ __global__ void __launch_bounds__(kThreads) fwd_simt_kernel(SimtArgs a) {
     float d = red_delta[0][t][c] + red_delta[1][t][c] + red_delta[2][t][c] + red_delta[3][t][c];
     float v = d;
     if (HAS_BASE) v = red_base[t][c] + load_coeff(a.coeff, a.coeff_dtype, r / a.m) * d;
-    if (a.splits == 1)
-      y[r * N + n] = F16<T>::from_f32(v);
-    else
+    if (a.splits == 1) {
+      if (a.fp32_out) reinterpret_cast<float*>(a.y)[r * N + n] = v;
+      else y[r * N + n] = F16<T>::from_f32(v);
+    } else
       a.partial[((int64_t)split * a.rows + r) * N + n] = v;
   }
   if (a.splits == 1) return;
@@ -187,7 +189,8 @@ __global__ void __launch_bounds__(kThreads) fwd_simt_kernel(SimtArgs a) {
     const int64_t r = r0 + t;
     float v = 0.f;
     for (int s = 0; s < a.splits; ++s) v += __ldcg(&a.partial[((int64_t)s * a.rows + r) * N + n]);
-    y[r * N + n] = F16<T>::from_f32(v);
+    if (a.fp32_out) reinterpret_cast<float*>(a.y)[r * N + n] = v;
+    else y[r * N + n] = F16<T>::from_f32(v);
   }
   if (tid == 0) a.counters[tile_id] = 0u;  // leave the workspace clean for the next launch
 }
@@ -244,6 +247,7 @@ int launch_fwd_simt(const FwdProblem& p) {
   a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + counters);
   a.rows = rows; a.m = p.m; a.K = p.K; a.N = p.N; a.mask_tenant_stride = p.mask_tenant_stride;
   a.splits = plan.splits; a.slabs_per_split = plan.slabs_per_split;
+  a.fp32_out = p.fp32_out ? 1 : 0;
   dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.splits, (unsigned)plan.row_chunks);
   const bool has_base = p.w != nullptr;
   if (p.dtype == BD_BF16) {

@@ -193,6 +193,8 @@ struct UmmaArgs {
   uint32_t stage_bytes, off_masks, off_x;     // stage layout: [W tile][masks][X tile]
   uint32_t off_xp, xp_buf_bytes;              // permuted activation tiles, one per A buffer
   uint32_t tx_bytes;
+  int static_ops;    // BD_FLAG_STATIC_OPERANDS: weight / sign tiles may be requested before griddepcontrol.wait
+  int fp32_out;      // BD_FLAG_FP32_OUT: y is fp32 (no rounding)
   int dbg;           // bring-up builds only (-DBD_BRINGUP): see dbg_flags() below; always 0 in the release library
   long long* trace;  // optional [64 units][16 slots] clock64 timestamps of CTA 0 (bring-up instrumentation)
 };
@@ -211,6 +213,12 @@ __device__ __forceinline__ constexpr int dbg_flags(const UmmaArgs&) { return 0; 
 template <bool TRACE>
 __device__ __forceinline__ void trace_mark(const UmmaArgs& a, int it, int slot) {
   if (TRACE && a.trace != nullptr && blockIdx.x == 0 && it < 64) a.trace[it * 16 + slot] = clock64();
+}
+// Output store: the activation dtype (one rounding), or fp32 partial sums for tensor-parallel shards (BD_FLAG_FP32_OUT).
+template <typename T16>
+__device__ __forceinline__ void store_y(T16* y, int64_t idx, float v, int fp32) {
+  if (fp32) reinterpret_cast<float*>(y)[idx] = v;
+  else y[idx] = F16<T16>::from_f32(v);
 }
 __device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return a.unit_quantum * (c * a.units_per_cta + min(c, a.units_rem)); }
 
@@ -394,7 +402,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // K-permuted copy of the activation rows for A buffer `b` (see the header comment): job = (row r, 16-byte output
   // chunk c of the 64-K block); out chunk c of a 32-group = x[4c..4c+3] interleaved with x[4c+16..4c+19]; source and
   // destination tiles use the 128-byte swizzle (chunk index XOR row % 8).
-  auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job) {
+  auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job, uint32_t& bucket_mask) {
     if constexpr (DELTA8) {
       // 8-bit delta path (one row per tenant).  job = (row r, 32-group g, c): one 32-bit output word per B-operand row,
       // holding K slots 4c..4c+3 of the group = activations k = c + 8q, q = 0..3 (the order the e4m3 sign registers are
@@ -409,6 +417,9 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       // B-operand row (15 of the tenant's 16 accumulator columns); an element is zero in the rows of the other buckets.
       // The epilogue adds sum_b 2^c_b * (d[3b] + d[3b+1] + d[3b+2]) in fp32.  |x| < 2^-60 degrades gradually (absolute error
       // < 2^-76 per element); |x| >= 2^60, inf and NaN become NaN pieces: the result is NaN, never a silently clipped number.
+      // Stores: a bucket's three words are written only if the bucket holds a non-zero element now or did the last time this
+      // job wrote this A buffer's tile (bucket_mask, kept by the caller per (job, A buffer); the tiles start zeroed) --
+      // real activation blocks live in one or two adjacent buckets, so 3-6 of the 15 (bank-conflicting) stores remain.
       const int r = job >> 4, g = (job >> 3) & 1, c = job & 7;
       const uint8_t* src = xsrc + r * 128 + 2 * (c & 7);
       float f[4];
@@ -440,18 +451,26 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       const int t = r;                               // one row per tenant on this path
       // tenant tile: [16 rows x 64 B] as 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
       uint8_t* tile = xp + t * 1024 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
+      uint32_t now_mask = 0;
 #pragma unroll
       for (int b = 0; b < kD8Buckets; ++b) {
         // byte q of the word goes to bucket b's rows iff element q is in bucket b: PRMT selector nibble q = q, else 4 (-> 0)
         const uint32_t ne = bsel ^ (0x1111u * b);
         const uint32_t nz = (ne | (ne >> 1) | (ne >> 2)) & 0x1111u;
         const uint32_t sel = (0x3210u & ~(nz * 7u)) | (nz << 2);
+        const uint32_t v0 = __byte_perm(pw[0], 0, sel);  // first piece: non-zero iff the element is (NaN marker included)
+        const uint32_t live = v0 != 0 ? 1u : 0u;
+        now_mask |= live << b;
+        if (live | ((bucket_mask >> b) & 1u)) {
+          const uint32_t v[3] = {v0, __byte_perm(pw[1], 0, sel), __byte_perm(pw[2], 0, sel)};
 #pragma unroll
-        for (int piece = 0; piece < 3; ++piece) {
-          const int rr = 3 * b + piece;
-          *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = __byte_perm(pw[piece], 0, sel);
+          for (int piece = 0; piece < 3; ++piece) {
+            const int rr = 3 * b + piece;
+            *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = v[piece];
+          }
         }
       }
+      bucket_mask = now_mask;
       return;
     }
     const int r = job >> 3, c = job & 7;
@@ -474,12 +493,15 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     if (lane == 0) {
       Ring st;
       UnitCursor cur{nt0, mc0, kb0};
-      // Prologue under PDL: the weight and sign tiles of the first `stages` units are static data and are requested
-      // right away; the activation tiles are produced by the previous kernel of the stream, so those loads are issued
-      // only after griddepcontrol.wait.  Each stage's barrier expects all three loads.
+      // Prologue under PDL: when the caller declares the weight and sign tiles static (BD_FLAG_STATIC_OPERANDS: long-lived
+      // module buffers) those of the first `stages` units are requested right away; the activation tiles are produced by
+      // the previous kernel of the stream, so those loads are issued only after griddepcontrol.wait.  Each stage's barrier
+      // expects all three loads.
       {
         const int npre = min(a.stages, u_end - u_begin);
         UnitCursor c2 = cur;
+        // Operands the caller did not declare static may have been written by the preceding kernel: everything waits.
+        if (!a.static_ops) asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int i = 0; i < npre; ++i) {
           uint8_t* sp = smem + (size_t)i * a.stage_bytes;
           mbar_arrive_expect_tx(&bar_full[i], a.tx_bytes);
@@ -587,15 +609,32 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // Released per unit by the sync warp (shared-memory counter); permutes / splits the activations while the unpack warps
     // convert the signs; arrives with them on the A buffer's named barrier.
     Ring st, ab;
+    // 8-bit path: live-bucket masks of this lane's (at most two) jobs, 5 bits per A buffer (see xperm_job)
+    unsigned long long bucket_state[2] = {0ull, 0ull};
+    uint32_t no_state = 0;
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
       wait_released(&s_released, u - u_begin);
       if (!NATK && !(dbg_flags(a) & (1 | 64))) {
         const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
         uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
-        // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
-        const int j0 = xperm_shared ? kUnpackWarps * 32 : 0, jstride = xperm_shared ? (kUnpackWarps + kXpermWarps) * 32 : kXpermWarps * 32;
-        for (int job = j0 + (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += jstride) xperm_job(xsrc, xp, job);
+        if constexpr (DELTA8) {
+          // at most T <= 10 tenants x 16 jobs: one or two jobs per lane, always the same ones
+          const int sh = 5 * ab.idx;
+#pragma unroll
+          for (int ji = 0; ji < 2; ++ji) {
+            const int job = (warp - kWarpXperm0) * 32 + lane + ji * kXpermWarps * 32;
+            if (job < xjobs) {
+              uint32_t mask = (uint32_t)(bucket_state[ji] >> sh) & 31u;
+              xperm_job(xsrc, xp, job, mask);
+              bucket_state[ji] = (bucket_state[ji] & ~(31ull << sh)) | ((unsigned long long)mask << sh);
+            }
+          }
+        } else {
+          // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
+          const int j0 = xperm_shared ? kUnpackWarps * 32 : 0, jstride = xperm_shared ? (kUnpackWarps + kXpermWarps) * 32 : kXpermWarps * 32;
+          for (int job = j0 + (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += jstride) xperm_job(xsrc, xp, job, no_state);
+        }
         fence_proxy_async();
       }
       if (warp == kWarpXperm0 && lane == 0) trace_mark<TRACE>(a, u - u_begin, 10);
@@ -728,7 +767,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const uint8_t* sp = smem + (size_t)st_i.idx * a.stage_bytes;
           if (!NATK && xperm_shared) {  // large row counts: the unpack warps share the activation permutation
             uint8_t* xp = smem + a.off_xp + (size_t)ab_i.idx * a.xp_buf_bytes;
-            for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) xperm_job(sp + a.off_x, xp, job);
+            for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) { uint32_t none = 0; xperm_job(sp + a.off_x, xp, job, none); }
           }
           unpack_unit(sp, ab_i.idx, grp, 2);
           st_i.advance(a.stages);
@@ -800,7 +839,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
             dsum = fmaf(d1[4] + d1[5] + d1[6], 0x1p45f, dsum);
             const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
             if (full_k) {
-              if (n < seg_n) y[(int64_t)t * seg_n + n] = F16<T16>::from_f32(v);
+              if (n < seg_n) store_y(y, (int64_t)t * seg_n + n, v, a.fp32_out);
             } else {
               part[(size_t)t * kTileN + row] = v;
             }
@@ -830,7 +869,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
               const int r = t * a.m + ii;
               const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
               if (full_k) {
-                if (n < seg_n) y[(int64_t)(r_off + r) * seg_n + n] = F16<T16>::from_f32(v);
+                if (n < seg_n) store_y(y, (int64_t)(r_off + r) * seg_n + n, v, a.fp32_out);
               } else {
                 part[(size_t)r * kTileN + row] = v;
               }
@@ -876,10 +915,14 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
                 for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
               }
               const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
-              T16* dst = y + (int64_t)(r_off + r) * seg_n + n4;
-              if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte aligned for these 4 elements
-                const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
-                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
+              const int64_t o4 = (int64_t)(r_off + r) * seg_n + n4;
+              if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte (fp32: 16-byte) aligned for these 4 elements
+                if (a.fp32_out) {
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o4) = acc;
+                } else {
+                  const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
+                  *reinterpret_cast<uint2*>(y + o4) = *reinterpret_cast<const uint2*>(o);
+                }
               }
             }
             if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
@@ -1155,6 +1198,8 @@ static int launch_one(const FwdProblem& p) {
   a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + kWsScratchOffset);
   a.trace = g_trace_buf;
   a.dbg = g_dbg_flags;
+  a.static_ops = p.static_operands ? 1 : 0;
+  a.fp32_out = p.fp32_out ? 1 : 0;
 
   const CUtensorMapDataType dt16 = p.dtype == BD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   alignas(64) UmmaMaps maps{};
@@ -1208,6 +1253,7 @@ int launch_fwd_umma(const FwdProblem& p0) {
   FwdProblem p = p0;
   if (p.mask_tenant_stride == 0 && p.T > 1) { p.m = p.T * p.m; p.T = 1; }
   const size_t esz = 2;  // bf16 / fp16
+  const size_t ysz = p.fp32_out ? 4 : esz;
   const size_t csz = p.coeff_dtype == BD_FP32 ? 4 : 2;
   const bool has_base = p.w != nullptr;
   if (p.nseg > 1) {
@@ -1237,7 +1283,7 @@ int launch_fwd_umma(const FwdProblem& p0) {
       FwdProblem s = p;
       s.T = (p.T - t0 < g) ? p.T - t0 : g;
       s.x = reinterpret_cast<const char*>(p.x) + (size_t)t0 * p.m * p.K * esz;
-      s.y = reinterpret_cast<char*>(p.y) + (size_t)t0 * p.m * p.N * esz;
+      s.y = reinterpret_cast<char*>(p.y) + (size_t)t0 * p.m * p.N * ysz;
       s.masks = p.masks + t0 * p.mask_tenant_stride;
       if (p.coeff) s.coeff = reinterpret_cast<const char*>(p.coeff) + (size_t)t0 * csz;
       int rc = launch_fwd_umma(s);
@@ -1251,7 +1297,7 @@ int launch_fwd_umma(const FwdProblem& p0) {
       FwdProblem s = p;
       s.m = (p.m - r0 < kMaxRows) ? p.m - r0 : kMaxRows;
       s.x = reinterpret_cast<const char*>(p.x) + (size_t)r0 * p.K * esz;
-      s.y = reinterpret_cast<char*>(p.y) + (size_t)r0 * p.N * esz;
+      s.y = reinterpret_cast<char*>(p.y) + (size_t)r0 * p.N * ysz;
       int rc = launch_one(s);
       if (rc) return rc;
     }

@@ -147,8 +147,10 @@ class SiblingGroup:
         key = (x.data_ptr(), ver, tuple(x.shape), x.dtype, x.device)
         if self._key != key or id(who) not in self._outs:
             T = who.mask.shape[0]
+            static = all(m.module.weight.is_contiguous() for m in self.members)  # a fresh copy is still queued on the stream
             ws = [m.module.weight if m.module.weight.is_contiguous() else m.module.weight.contiguous() for m in self.members]
-            ys = _fused_forward_grouped(x, ws, [m.mask for m in self.members], [m.coeff for m in self.members], T, who.kernel)
+            ys = _fused_forward_grouped(x, ws, [m.mask for m in self.members], [m.coeff for m in self.members], T, who.kernel,
+                                        static_operands=static)
             self._key, self._x = key, x
             self._outs = {id(m): y for m, y in zip(self.members, ys)}
         y = self._outs.pop(id(who))
@@ -204,9 +206,10 @@ class DiffCompressModule(nn.Module):
         if self._group is not None and x.is_cuda:
             return self._group.forward_for(self, x)
         w = self.module.weight
-        if not w.is_contiguous():
+        static = w.is_contiguous()  # module-owned buffers; a fresh .contiguous() copy is still queued on the stream
+        if not static:
             w = w.contiguous()
-        y = _fused_forward(x, w, self.mask, self.coeff, T, self.kernel)
+        y = _fused_forward(x, w, self.mask, self.coeff, T, self.kernel, static_operands=static)
         if getattr(self.module, "bias", None) is not None:
             y = y + self.module.bias
         return y

@@ -19,8 +19,13 @@ from . import _lib
 from .binary_gemm_kernel import pack, unpack  # noqa: F401  (re-exported like the reference module)
 
 
-def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coeff: torch.Tensor, T: int, kernel="auto") -> torch.Tensor:
-    """x: (T, m, K) contiguous; w_nk: (N, K) contiguous; masks: (K/32, N) or (T, K/32, N) int32; coeff: (T,) or 0-dim."""
+def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coeff: torch.Tensor, T: int, kernel="auto",
+                   static_operands: bool = False, out_fp32: bool = False) -> torch.Tensor:
+    """x: (T, m, K) contiguous; w_nk: (N, K) contiguous; masks: (K/32, N) or (T, K/32, N) int32; coeff: (T,) or 0-dim.
+
+    ``static_operands``: w_nk and masks are long-lived buffers that nothing queued on the stream is still writing
+    (BD_FLAG_STATIC_OPERANDS: the launch may prefetch them while the stream's preceding kernel drains).  ``out_fp32``:
+    return the unrounded fp32 sums (BD_FLAG_FP32_OUT; tensor-parallel partials)."""
     if not x.is_cuda:
         raise RuntimeError(
             "bitdelta_b200: the fused BinaryDiff forward is implemented only as sm_100a CUDA kernels "
@@ -42,7 +47,7 @@ def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coe
         coeff = coeff.expand(T)
     coeff = coeff.contiguous()
     assert coeff.numel() == T
-    y = torch.empty((T, m, N), device=x.device, dtype=x.dtype)
+    y = torch.empty((T, m, N), device=x.device, dtype=torch.float32 if out_fp32 else x.dtype)
     if y.numel() == 0:
         return y
     with torch.cuda.device(x.device):
@@ -50,16 +55,16 @@ def _fused_forward(x: torch.Tensor, w_nk: torch.Tensor, masks: torch.Tensor, coe
         _lib.check(
             _lib.lib.bd_binarydiff_fwd_batched(
                 x.data_ptr(), w_nk.data_ptr(), masks.data_ptr(), coeff.data_ptr(), _lib.dtype_code(coeff.dtype), y.data_ptr(),
-                _lib.dtype_code(x.dtype), T, m, K, N, stride, ws.data_ptr(), ws.numel(), _lib.kernel_code(kernel),
-                _lib.stream_ptr(x.device),
+                _lib.dtype_code(x.dtype), T, m, K, N, stride, ws.data_ptr(), ws.numel(),
+                _lib.kernel_code(kernel, static_operands, out_fp32), _lib.stream_ptr(x.device),
             )
         )
     return y
 
 
-def _fused_forward_grouped(x: torch.Tensor, weights, masks_list, coeffs, T: int, kernel="auto"):
+def _fused_forward_grouped(x: torch.Tensor, weights, masks_list, coeffs, T: int, kernel="auto", static_operands: bool = False):
     """Several BinaryDiff linears on the SAME activations in one launch (q/k/v, gate/up).  x: (T, m, K); weights[s]: (N_s, K);
-    masks_list[s]: (T, K/32, N_s) int32; coeffs[s]: (T,).  Returns [y_s (T, m, N_s)]."""
+    masks_list[s]: (T, K/32, N_s) int32; coeffs[s]: (T,).  Returns [y_s (T, m, N_s)].  ``static_operands`` as in _fused_forward."""
     import ctypes
 
     if not x.is_cuda:
@@ -91,7 +96,8 @@ def _fused_forward_grouped(x: torch.Tensor, weights, masks_list, coeffs, T: int,
         _lib.check(
             _lib.lib.bd_binarydiff_fwd_grouped(
                 x.data_ptr(), nseg, arr(weights), arr(masks_list), arr(cs), _lib.dtype_code(cdt), arr(ys), i64(Ns), i64(strides),
-                _lib.dtype_code(x.dtype), T, m, K, ws.data_ptr(), ws.numel(), _lib.kernel_code(kernel), _lib.stream_ptr(x.device),
+                _lib.dtype_code(x.dtype), T, m, K, ws.data_ptr(), ws.numel(), _lib.kernel_code(kernel, static_operands),
+                _lib.stream_ptr(x.device),
             )
         )
     return ys
@@ -172,15 +178,19 @@ class BinaryDiff(nn.Module):
         )
         self._w_cache = None
 
-    def _weight_nk(self) -> torch.Tensor:
-        """[N, K] row-major view of the base weight (zero-copy while ``base`` keeps the reference's (1, K) strides)."""
+    def _weight_nk(self, with_static: bool = False):
+        """[N, K] row-major view of the base weight (zero-copy while ``base`` keeps the reference's (1, K) strides).
+        ``with_static`` also returns whether the tensor is a long-lived buffer (False right after a copy was made: the
+        copy kernel is still queued on the stream, so the forward must not prefetch it early)."""
         w = self.base.t()
-        if w.is_contiguous():
-            return w
-        key = (self.base.data_ptr(), 0 if self.base.is_inference() else self.base._version, self.base.device)
-        if self._w_cache is None or self._w_cache[0] != key:
-            self._w_cache = (key, w.contiguous())
-        return self._w_cache[1]
+        static = True
+        if not w.is_contiguous():
+            key = (self.base.data_ptr(), 0 if self.base.is_inference() else self.base._version, self.base.device)
+            if self._w_cache is None or self._w_cache[0] != key:
+                self._w_cache = (key, w.contiguous())
+                static = False
+            w = self._w_cache[1]
+        return (w, static) if with_static else w
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         # [B, seq, in] @ [in, out] + coeff * ([B, seq, in] @ sign[in, out])   (diff.py:33-39)
@@ -189,7 +199,8 @@ class BinaryDiff(nn.Module):
         if torch.is_grad_enabled() and (rows.requires_grad or self.coeff.requires_grad):
             y = _BinaryDiffFunction.apply(rows, self._weight_nk(), self.mask, self.coeff, self.kernel, self.delta_grad_x)
         else:
-            y = _fused_forward(rows, self._weight_nk(), self.mask, self.coeff, 1, self.kernel)
+            w, static = self._weight_nk(with_static=True)
+            y = _fused_forward(rows, w, self.mask, self.coeff, 1, self.kernel, static_operands=static)
         return y.reshape(*lead, y.shape[-1])
 
 

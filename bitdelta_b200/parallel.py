@@ -94,10 +94,10 @@ class TensorParallelDiffLinear(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         # x: [T, m, K_shard]
         T = self.mask.shape[0]
-        y = _fused_forward(x.contiguous(), self.weight, self.mask, self.coeff, T, self.kernel)
         if self.mode == "row" and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            # decode-size payloads ([T*m, hidden] elements): sum the partials in fp32 to keep 1e-3 parity
-            y32 = y.float()
+            # The kernel hands back its UNROUNDED fp32 partial sums (BD_FLAG_FP32_OUT); they are summed across the ranks in
+            # fp32 and rounded once, like the unsharded kernel rounds its fp32 accumulator once.
+            y32 = _fused_forward(x.contiguous(), self.weight, self.mask, self.coeff, T, self.kernel, static_operands=True, out_fp32=True)
             dist.all_reduce(y32, op=dist.ReduceOp.SUM, group=self.group)
-            y = y32.to(y.dtype)
-        return y
+            return y32.to(x.dtype)
+        return _fused_forward(x.contiguous(), self.weight, self.mask, self.coeff, T, self.kernel, static_operands=True)

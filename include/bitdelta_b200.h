@@ -51,6 +51,22 @@ enum bd_kernel {
   BD_KERNEL_UMMA = 2  /* tcgen05/TMEM/TMA kernel: fails with BD_ERR_UNSUPPORTED if the shape does not qualify */
 };
 
+/* Launch flags, OR-ed into the `kernel` argument of the forward entry points (bits 8 and up; the low byte is bd_kernel).
+ *
+ * BD_FLAG_STATIC_OPERANDS: the caller guarantees that `w` and the sign words were NOT written by work that precedes
+ *   this call on `stream` since the last synchronisation point (long-lived weights: BinaryDiff / DiffCompressModule
+ *   buffers).  The tcgen05 kernel is launched with programmatic dependent launch; with this flag it requests its first
+ *   weight / sign tiles while the preceding kernel of the stream is still draining.  WITHOUT the flag every load is issued
+ *   after griddepcontrol.wait, so operands produced by the immediately preceding kernel -- binary_bmm(a, pack(b)) from the
+ *   reference's notebook, a freshly made .contiguous() copy -- are always seen.  Activations `x` are never prefetched.
+ * BD_FLAG_FP32_OUT: y is written as fp32 [T,m,N] (no rounding to `dtype`): the partial sums of a row-parallel
+ *   tensor-parallel shard, reduced across ranks in fp32 and rounded once (bitdelta_b200/parallel.py).
+ */
+enum bd_launch_flag {
+  BD_FLAG_STATIC_OPERANDS = 1 << 8,
+  BD_FLAG_FP32_OUT = 1 << 9
+};
+
 BD_API int bd_abi_version(void);
 BD_API const char* bd_last_error(void);
 

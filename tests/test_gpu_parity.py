@@ -818,3 +818,163 @@ def test_non_finite_and_out_of_range_activations_are_not_clipped():
             others = [i for i in range(T) if i != t]
             assert torch.isfinite(y[others]).all()
         assert torch.equal(mod(xb)[others], y_ref[others])
+
+
+def test_bucket_set_changes_from_block_to_block():
+    # The 8-bit decode path rewrites only the exponent buckets that are live now or were live the last time the same
+    # A-buffer tile was written.  Here every 64-wide K block has its own magnitude (some blocks are all zero), so the live
+    # set changes with every unit and stale pieces of an earlier unit would show up as an error.
+    T, m, K, N = 6, 1, 8192, 640
+    gen, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 17)
+    expo = torch.tensor([-12.0, -6.0, 0.0, 6.0, 11.0], device=DEV)[torch.randint(0, 5, (T, K // 64), generator=gen, device=DEV)]
+    blk = torch.pow(10.0, expo) * (torch.rand(T, K // 64, generator=gen, device=DEV) > 0.2)  # a fifth of the blocks is zero
+    x = (x * blk.repeat_interleave(64, dim=1)[:, None, :]).bfloat16()
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact_d = torch.bmm(x.double(), signs)
+    for kernel in ("umma", "simt"):
+        c = bd.binary_bmm(x, masks, kernel=kernel)
+        assert_close_to_exact(c, exact_d.cpu().numpy(), f"binary_bmm per-block scales ({kernel})")
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, (coeffs.float() * 300).bfloat16())
+    mod.kernel = "umma"
+    y1, y2 = mod(x), mod(x)
+    exact = x.double() @ w.double().T + mod.coeff.double()[:, None, None] * exact_d
+    assert_close_to_exact(y1, exact.cpu().numpy(), "DiffCompressModule per-block scales")
+    assert torch.equal(y1, y2)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE shapes
+# Every (N, K) of the models BASELINE.json names, through the reference-named modules, against the float64 truth built from
+# the bit-exact unpack: Llama-2-7B (config 2, one delta: BinaryDiff at decode and prefill sizes), Llama-2-13B + 4 deltas
+# (config 4), Llama-2-70B + 8 deltas as the per-rank shards of an 8-way tensor-parallel split (config 5: column-parallel
+# q/k/v/gate/up slice N, row-parallel o/down slice K).
+def _exact_forward(x, w, masks, coeffs):
+    signs = bd.unpack(masks).double() * 2 - 1
+    d = torch.bmm(x.double(), signs) if masks.dim() == 3 else x.double() @ signs
+    c = coeffs.double().reshape(-1)
+    return x.double() @ w.double().T + (c[:, None, None] if masks.dim() == 3 else c) * d
+
+
+@pytest.mark.parametrize("N,K", [(4096, 4096), (11008, 4096), (4096, 11008)])
+@pytest.mark.parametrize("rows", [1, 2048])
+def test_llama2_7b_shapes_binarydiff(N, K, rows):
+    gen = torch.Generator(device=DEV).manual_seed(N * 3 + K + rows)
+    base = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    fine = (base.float() + torch.randn(N, K, generator=gen, device=DEV) * 0.002).bfloat16()
+    mod = bd.BinaryDiff(base, fine)
+    assert bd._lib.lib.bd_select_kernel(bd._lib.BD_BF16, 1, rows, K, N, 1) == bd._lib.KERNEL_UMMA
+    x = torch.randn(1, rows, K, generator=gen, device=DEV).bfloat16()
+    with torch.no_grad():
+        y = mod(x)
+    exact = _exact_forward(x[0], base, mod.mask, mod.coeff.detach())
+    assert_close_to_exact(y[0], exact.cpu().numpy(), f"llama-2-7b {N}x{K} rows {rows}")
+
+
+@pytest.mark.parametrize("N,K,T,m", [
+    (5120, 5120, 4, 1), (13824, 5120, 4, 1), (5120, 13824, 4, 1), (5120, 5120, 4, 64),       # Llama-2-13B + 4 deltas
+    (1024, 8192, 8, 1), (128, 8192, 8, 1), (3584, 8192, 8, 1), (8192, 1024, 8, 1), (8192, 3584, 8, 1),  # 70B, TP = 8 shards
+    (8192, 8192, 8, 1), (28672 // 4, 8192, 8, 1),                                            # 70B, TP = 1 / 4
+])
+def test_llama2_13b_and_70b_shard_shapes(N, K, T, m):
+    gen = torch.Generator(device=DEV).manual_seed(N + 7 * K + T)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.003 + 0.0005).bfloat16()
+    x = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    y = mod(x)
+    exact = _exact_forward(x, w, masks, coeffs)
+    assert_close_to_exact(y, exact.cpu().numpy(), f"{N}x{K} T={T} m={m}")
+
+
+def test_multi_tenant_prefill_13b():
+    # config 4: prefill of a few hundred tokens per tenant through the 13B attention projection (the full 4096-token
+    # prefill is the same code path, one 128-row chunk after the other)
+    N, K, T, m = 5120, 5120, 4, 300
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.003 + 0.0005).bfloat16()
+    x = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    y = bd.DiffCompressModule(lin, masks, coeffs)(x)
+    assert_close_to_exact(y, _exact_forward(x, w, masks, coeffs).cpu().numpy(), "13B multi-tenant prefill")
+
+
+# ------------------------------------------------------------------------------------------------ launch flags
+@pytest.mark.parametrize("kernel", ["umma", "simt"])
+@pytest.mark.parametrize("T,m,K,N", [(8, 1, 1024, 8192), (2, 40, 512, 384), (1, 300, 1024, 512)])
+def test_fp32_partial_sum_output(kernel, T, m, K, N):
+    # BD_FLAG_FP32_OUT: the unrounded fp32 sums (row-parallel tensor-parallel shards); rounding them gives the normal output
+    from bitdelta_b200.diff import _fused_forward
+
+    gen, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 23)
+    x = x.bfloat16()
+    y32 = _fused_forward(x, w, masks, coeffs, T, kernel, out_fp32=True)
+    y16 = _fused_forward(x, w, masks, coeffs, T, kernel)
+    assert y32.dtype == torch.float32 and y32.shape == y16.shape
+    assert torch.equal(y32.bfloat16(), y16)
+    exact = _exact_forward(x, w, masks, coeffs)
+    rel = ((y32.double() - exact).abs().mean() / exact.abs().mean()).item()
+    assert rel < 1e-5, rel  # fp32 accumulation only
+
+
+def test_operands_written_by_the_preceding_kernel_are_seen():
+    # binary_bmm(a, pack(b)) (the reference notebook's call pattern) and freshly copied weights are produced by
+    # the kernel right before the forward on the same stream; without BD_FLAG_STATIC_OPERANDS the launch must not prefetch
+    # them ahead of that kernel.  Alternate two different operand sets in one buffer, back to back.
+    T, m, K, N = 6, 1, 4096, 4096
+    gen = torch.Generator(device=DEV).manual_seed(29)
+    a = torch.randn(T, m, K, generator=gen, device=DEV).bfloat16()
+    bits = [torch.rand(T, K, N, generator=gen, device=DEV) > 0.5 for _ in range(2)]
+    want = [torch.bmm(a.double(), b.double() * 2 - 1) for b in bits]
+    for i in range(12):
+        c = bd.binary_bmm(a, bd.pack(bits[i % 2]), kernel="umma")
+        assert_close_to_exact(c, want[i % 2].cpu().numpy(), f"iteration {i}")
+    w2 = [(torch.randn(N, K, generator=gen, device=DEV) * 0.02).bfloat16() for _ in range(2)]
+    masks = bd.pack(bits[0])
+    coeffs = torch.full((T,), 0.002, device=DEV)
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    buf = torch.empty(K, N, device=DEV, dtype=torch.bfloat16)
+    for i in range(8):
+        buf.copy_(w2[i % 2].T)
+        lin.weight.data = buf.T  # non-contiguous view: forward makes a fresh contiguous copy on the stream
+        y = mod(a)
+        exact = _exact_forward(a, w2[i % 2], masks, coeffs)
+        assert_close_to_exact(y, exact.cpu().numpy(), f"weight copy {i}")
+
+
+def test_captured_graph_survives_a_larger_eager_call():
+    # the per-stream workspace is allocated once at its maximum; a decode graph captured first keeps working after
+    # a prefill-sized eager call on the same stream (the workspace used to be re-allocated, leaving the graph a stale pointer)
+    T, K, N = 6, 4096, 1024
+    _, w, masks, coeffs, x = _tenant_problem(T, 1, K, N, 31)
+    x = x.bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y_eager = mod(x).clone()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            y_graph = mod(x)
+        ws_before = bd._lib.workspace(DEV, 6, N).data_ptr()
+        big = torch.randn(1, 2000, K, device=DEV).bfloat16()
+        fine = (w.float() + 0.002 * torch.randn_like(w.float())).bfloat16()
+        with torch.no_grad():
+            bd.BinaryDiff(w, fine)(big)
+        assert bd._lib.workspace(DEV, 2000, N).data_ptr() == ws_before
+        for _ in range(3):
+            graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_graph, y_eager)

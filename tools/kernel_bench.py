@@ -29,12 +29,12 @@ for (T, m, K, N) in shapes:
     reps = max(n_sets, 16)
     with torch.cuda.stream(s):
         for i in range(n_sets):
-            _fused_forward(x, ws[i], ms[i], coeff, T, kernel)
+            _fused_forward(x, ws[i], ms[i], coeff, T, kernel, static_operands=True)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=s):
             for i in range(reps):
-                _fused_forward(x, ws[i % n_sets], ms[i % n_sets], coeff, T, kernel)
+                _fused_forward(x, ws[i % n_sets], ms[i % n_sets], coeff, T, kernel, static_operands=True)
         for _ in range(3):
             gr.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

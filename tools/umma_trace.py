@@ -15,13 +15,13 @@ ms = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=g, device=dev
 coeff = torch.full((T,), 0.002, device=dev)
 x = torch.randn(T, m, K, generator=g, device=dev).bfloat16()
 for _ in range(3):
-    _fused_forward(x, w, ms, coeff, T, "umma")
+    _fused_forward(x, w, ms, coeff, T, "umma", static_operands=True)
 buf = torch.zeros(64 * 16 + 4 * 160, dtype=torch.int64, device=dev)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 _lib.lib.bd_debug_set_trace(buf.data_ptr())
-_fused_forward(x, w, ms, coeff, T, "umma")
+_fused_forward(x, w, ms, coeff, T, "umma", static_operands=True)
 ev0.record()
-_fused_forward(x, w, ms, coeff, T, "umma")
+_fused_forward(x, w, ms, coeff, T, "umma", static_operands=True)
 ev1.record()
 torch.cuda.synchronize()
 print(f"event time of one traced launch: {ev0.elapsed_time(ev1)*1e3:.1f} us")
