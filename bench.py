@@ -200,8 +200,84 @@ def workload_config(world: int):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def build_model(torch, bd, dev, layers: int, seed: int, grouped: bool = True):
-    """Random-init Mistral-7B-shaped stack of DiffCompressModules on `dev`."""
+def load_reference_gpu_modules():
+    """The reference's OWN GPU path, unmodified, from baseline/_ref (pip-installed from /root/reference):
+    `binary_bmm` (Triton, bitdelta/binary_gemm_kernel.py:297-335) and the `DiffCompressModule` class body of
+    demo/demo_backend.py:82-98 (the demo file itself cannot be imported: it loads Mistral-7B at module level, :23)."""
+    import ast
+    import importlib.util
+
+    import torch
+    import torch.nn as nn
+
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    spec = importlib.util.spec_from_file_location("_ref_binary_gemm_kernel", os.path.join(ref_root, "bitdelta", "binary_gemm_kernel.py"))
+    kmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kmod)
+    src = open(os.path.join(ref_root, "demo", "demo_backend.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "DiffCompressModule")
+    ns = {"torch": torch, "nn": nn, "binary_bmm": kmod.binary_bmm}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "baseline/_ref/demo/demo_backend.py", "exec"), ns)
+    return ns["DiffCompressModule"], kmod
+
+
+def run_triton_reference(torch, mods, xs, y_ours, stream, dev, steps: int):
+    """Times the reference's DiffCompressModule stack (cuBLAS nn.Linear + Triton binary_bmm + two pointwise kernels per
+    linear) on the SAME weights, sign words and activations as our arm, under the same CUDA-graph replay harness."""
+    try:
+        RefModule, _ = load_reference_gpu_modules()
+    except Exception as e:  # baseline/_ref missing or triton import failure
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    x_h, x_a, x_m = xs
+    try:
+        with torch.cuda.stream(stream):
+            ref = [{name: RefModule(m.module, m.mask, m.coeff) for name, m in layer.items()} for layer in mods]
+
+            def step():
+                y = None
+                for layer in ref:
+                    layer["q_proj"](x_h); layer["k_proj"](x_h); layer["v_proj"](x_h)
+                    layer["o_proj"](x_a)
+                    layer["gate_proj"](x_h); layer["up_proj"](x_h)
+                    y = layer["down_proj"](x_m)
+                return y
+
+            t0 = time.perf_counter()
+            y_ref = step()  # Triton autotunes each (M, N, K) on its first call
+            torch.cuda.synchronize(dev)
+            tune_s = time.perf_counter() - t0
+            step()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                y_static = step()
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                graph.replay()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            rel = ((y_ours.float() - y_ref.float()).abs().mean() / y_ref.float().abs().mean()).item()
+        return {"ms_per_step": ms, "tokens_s": TENANTS / (ms * 1e-3), "steps": steps, "harness": "CUDA graph replay, same weights / signs / activations as `value`",
+                "path": "baseline/_ref: demo_backend.DiffCompressModule (nn.Linear cuBLAS + Triton binary_bmm + 2 pointwise), 224 linears per step, ungrouped",
+                "launches_per_step": 224 * 4, "rel_ours_vs_reference": rel, "autotune_s": tune_s}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def _group(bd, layer):
+    # what bd.fuse_sibling_projections does on a real decoder layer: projections the layer calls back to back on the same
+    # hidden states share one launch
+    bd.group_projections([layer["q_proj"], layer["k_proj"], layer["v_proj"]])
+    bd.group_projections([layer["gate_proj"], layer["up_proj"]])
+
+
+def build_model(torch, bd, dev, layers: int, seed: int, grouped: bool = True, tenants: int = TENANTS):
+    """Random-init Mistral-7B-shaped stack of DiffCompressModules with `tenants` deltas on `dev`."""
     gen = torch.Generator(device=dev).manual_seed(seed)
     mods = []
     for _ in range(layers):
@@ -210,16 +286,168 @@ def build_model(torch, bd, dev, layers: int, seed: int, grouped: bool = True):
             lin = torch.nn.Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16)
             with torch.no_grad():
                 lin.weight.normal_(0.0, 0.02, generator=gen)
-            masks = torch.randint(-(2**31), 2**31 - 1, (TENANTS, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
-            coeffs = (torch.rand(TENANTS, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
+            masks = torch.randint(-(2**31), 2**31 - 1, (tenants, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            coeffs = (torch.rand(tenants, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
             layer[name] = bd.DiffCompressModule(lin, masks, coeffs)
         if grouped:
-            # what bd.fuse_sibling_projections does on a real decoder layer: projections the layer calls back to back on
-            # the same hidden states share one launch
-            bd.group_projections([layer["q_proj"], layer["k_proj"], layer["v_proj"]])
-            bd.group_projections([layer["gate_proj"], layer["up_proj"]])
+            _group(bd, layer)
         mods.append(layer)
     return mods
+
+
+def tenant_slice(bd, mods, tenants: int, grouped: bool = True):
+    """The same stack serving only its first `tenants` deltas: new wrappers over leading slices (views) of the stacked sign
+    words and coefficients -- what a rank of a tenant-sharded deployment holds."""
+    out = []
+    for layer in mods:
+        sub = {name: bd.DiffCompressModule(m.module, m.mask[:tenants], m.coeff[:tenants]) for name, m in layer.items()}
+        if grouped:
+            _group(bd, sub)
+        out.append(sub)
+    return out
+
+
+def mistral_step(layer_mods, x_h, x_a, x_m):
+    y = None
+    for layer in layer_mods:
+        layer["q_proj"](x_h); layer["k_proj"](x_h); layer["v_proj"](x_h)
+        layer["o_proj"](x_a)
+        layer["gate_proj"](x_h); layer["up_proj"](x_h)
+        y = layer["down_proj"](x_m)
+    return y
+
+
+def graph_time_ms(torch, fn, stream, dev, steps: int, warmup: int, barrier=None):
+    """Captures fn() in a CUDA graph on `stream` (fn has been run eagerly before) and returns (ms per replay, result)."""
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        out = fn()
+    for _ in range(warmup):
+        graph.replay()
+    (barrier or (lambda: torch.cuda.synchronize(dev)))()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        graph.replay()
+    e1.record(stream)
+    (barrier or (lambda: torch.cuda.synchronize(dev)))()
+    return e0.elapsed_time(e1) / steps, out
+
+
+# Llama-2-70B decoder layer (BASELINE config 5): (name, N_out, K_in, tensor-parallel mode)
+LLAMA70B_LINEARS = [
+    ("q_proj", 8192, 8192, "column"), ("k_proj", 1024, 8192, "column"), ("v_proj", 1024, 8192, "column"), ("o_proj", 8192, 8192, "row"),
+    ("gate_proj", 28672, 8192, "column"), ("up_proj", 28672, 8192, "column"), ("down_proj", 8192, 28672, "row"),
+]
+TP_TENANTS = 8
+
+
+def run_tp(torch, bd, dist, dev, rank: int, world: int, stream, steps: int, warmup: int, barrier, tp_layers: int):
+    """BASELINE config 5: Llama-2-70B + 8 deltas decoder layers, every BinaryDiff linear split Megatron-style over the
+    `world` ranks (column-parallel q/k/v/gate/up: slices of N; row-parallel o/down: slices of K) with ONE sum all-reduce
+    of the fp32 partials after each row-parallel linear (2 per layer).  Times `tp_layers` layers per step (weights + signs
+    per rank exceed L2), with and without the collectives, and checks layer 0 against the unsharded modules."""
+    from bitdelta_b200.diff import _fused_forward, _fused_forward_grouped
+    from bitdelta_b200.parallel import TensorParallelDiffLinear, split_column_parallel, split_row_parallel
+
+    T = TP_TENANTS
+    gen = torch.Generator(device=dev).manual_seed(777)  # same seed on every rank: identical full tensors, sharded locally
+    layers, check = [], None
+    for li in range(tp_layers):
+        layer = {}
+        for name, n, k, mode in LLAMA70B_LINEARS:
+            w = torch.empty(n, k, device=dev, dtype=torch.bfloat16).normal_(0.0, 0.02, generator=gen)
+            masks = torch.randint(-(2**31), 2**31 - 1, (T, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            coeffs = (torch.rand(T, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
+            ws, ms = (split_column_parallel if mode == "column" else split_row_parallel)(w, masks, rank, world)
+            layer[name] = TensorParallelDiffLinear(ws, ms, coeffs, mode)
+            if li == 0 and mode == "row":
+                check = check or {}
+                check[name] = (w, masks, coeffs)
+            del w, masks
+        layers.append(layer)
+    x_h = torch.randn(T, 1, 8192, generator=gen, device=dev).bfloat16()
+    x_a_full = torch.randn(T, 1, 8192, generator=gen, device=dev).bfloat16()
+    x_m_full = torch.randn(T, 1, 28672, generator=gen, device=dev).bfloat16()
+    x_a = x_a_full[..., rank * 8192 // world:(rank + 1) * 8192 // world].contiguous()
+    x_m = x_m_full[..., rank * 28672 // world:(rank + 1) * 28672 // world].contiguous()
+
+    def col(layer, names, x):
+        ms_ = [layer[nm] for nm in names]
+        return _fused_forward_grouped(x, [m.weight for m in ms_], [m.mask for m in ms_], [m.coeff for m in ms_], T, "auto", static_operands=True)
+
+    def step(reduce: bool):
+        y = None
+        for layer in layers:
+            col(layer, ("q_proj", "k_proj", "v_proj"), x_h)
+            if reduce:
+                layer["o_proj"](x_a)
+            else:
+                _fused_forward(x_a, layer["o_proj"].weight, layer["o_proj"].mask, layer["o_proj"].coeff, T, "auto", static_operands=True, out_fp32=True).to(torch.bfloat16)
+            col(layer, ("gate_proj", "up_proj"), x_h)
+            if reduce:
+                y = layer["down_proj"](x_m)
+            else:
+                y = _fused_forward(x_m, layer["down_proj"].weight, layer["down_proj"].mask, layer["down_proj"].coeff, T, "auto", static_operands=True, out_fp32=True).to(torch.bfloat16)
+        return y
+
+    with torch.cuda.stream(stream):
+        # parity of the sharded row-parallel linears against the unsharded module (layer 0, every rank holds the full tensors)
+        parity = {}
+        for name, xf, xs in (("o_proj", x_a_full, x_a), ("down_proj", x_m_full, x_m)):
+            w, masks, coeffs = check[name]
+            lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False, device=dev, dtype=torch.bfloat16)
+            lin.weight.data = w
+            y_full = bd.DiffCompressModule(lin, masks, coeffs)(xf)
+            y_tp = layers[0][name](xs)
+            torch.cuda.synchronize(dev)
+            parity[name] = {"mean_rel": ((y_tp.float() - y_full.float()).abs().mean() / y_full.float().abs().mean()).item(),
+                            "bit_equal_frac": (y_tp == y_full).float().mean().item()}
+        check = None
+        torch.cuda.empty_cache()
+        step(True); step(False)
+        torch.cuda.synchronize(dev)
+        ms_with, _ = graph_time_ms(torch, lambda: step(True), stream, dev, steps, warmup, barrier)
+        ms_without, _ = graph_time_ms(torch, lambda: step(False), stream, dev, steps, warmup, barrier)
+    t = torch.tensor([ms_with, ms_without], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_with, ms_without = t[0].item(), t[1].item()
+    per_rank_bytes = sum(2 * n * k + T * n * k // 8 for _, n, k, _ in LLAMA70B_LINEARS) // world
+    us_layer = ms_with * 1e3 / tp_layers
+    return {
+        "workload": f"Llama-2-70B + {T} deltas decoder layers, tensor-parallel x{world}: column-parallel q/k/v (one launch) and gate/up (one launch), row-parallel o and down, {T} tenants x 1 token",
+        "layers_per_step": tp_layers, "us_per_layer": us_layer, "us_per_layer_without_collectives": ms_without * 1e3 / tp_layers,
+        "allreduce_us_each": (ms_with - ms_without) * 1e3 / (2 * tp_layers), "allreduces_per_layer": 2 if world > 1 else 0,
+        "collective_share_of_layer": (ms_with - ms_without) / ms_with if world > 1 else 0.0,
+        "collective": "NCCL all-reduce of the kernel's fp32 partial sums [8, 8192], one rounding after the sum" if world > 1 else "none (tp = 1)",
+        "tokens_s_80_layers": T / (us_layer * 80 * 1e-6), "per_rank_bytes_per_layer": per_rank_bytes,
+        "hbm_gbps_per_rank": per_rank_bytes / (us_layer * 1e-6) / 1e9, "parity_vs_unsharded": parity,
+    }
+
+
+def run_tenant_strong(torch, bd, dist, dev, rank, world, mods, stream, steps, warmup, barrier, grouped, gen):
+    """Strong scaling of tenant sharding: a FIXED set of 8 tenants split over the ranks (8 / world each), every rank still
+    streaming its whole W_base replica -- the sub-linear curve SURVEY.md 8e predicts (per-GPU bytes 2NK + (T/G) NK/8)."""
+    total = 8
+    if total % world != 0:
+        return None
+    t_local = total // world
+    sub = tenant_slice(bd, mods, t_local, grouped)
+    x_h = torch.randn(t_local, 1, 4096, generator=gen, device=dev).bfloat16()
+    x_a = torch.randn(t_local, 1, 4096, generator=gen, device=dev).bfloat16()
+    x_m = torch.randn(t_local, 1, 14336, generator=gen, device=dev).bfloat16()
+    with torch.cuda.stream(stream):
+        mistral_step(sub, x_h, x_a, x_m)
+        torch.cuda.synchronize(dev)
+        ms, _ = graph_time_ms(torch, lambda: mistral_step(sub, x_h, x_a, x_m), stream, dev, steps, warmup, barrier)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t[0].item()
+    return {"tenants_total": total, "tenants_per_gpu": t_local, "ms_per_step": ms, "tokens_s": total / (ms * 1e-3), "scaling": "strong",
+            "bytes_per_gpu_per_step": step_bytes(t_local, 1, len(mods)),
+            "hbm_frac_per_gpu": step_bytes(t_local, 1, len(mods)) / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
 
 
 def run_ours(args, rank: int, local_rank: int, world: int):
@@ -240,7 +468,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
 
     layers = args.layers
-    mods = build_model(torch, bd, dev, layers, seed=1234 + rank, grouped=not args.no_group)
+    # the strong-scaling leg serves 8 tenants in total: only a single GPU needs more than the headline's 6 resident
+    t_build = max(TENANTS, 8 // world) if not args.no_extras else TENANTS
+    mods_all = build_model(torch, bd, dev, layers, seed=1234 + rank, grouped=not args.no_group, tenants=t_build)
+    mods = mods_all if t_build == TENANTS else tenant_slice(bd, mods_all, TENANTS, grouped=not args.no_group)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     # static synthetic activations (one new token per tenant); outputs are not chained because the omitted norms
     # would be needed to keep magnitudes bounded
@@ -251,13 +482,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     host_out = torch.empty(TENANTS, 1, 4096, dtype=torch.bfloat16).pin_memory()
 
     def step():
-        y = None
-        for layer in mods:
-            layer["q_proj"](x_h); layer["k_proj"](x_h); layer["v_proj"](x_h)
-            layer["o_proj"](x_a)
-            layer["gate_proj"](x_h); layer["up_proj"](x_h)
-            y = layer["down_proj"](x_m)
-        return y
+        return mistral_step(mods, x_h, x_a, x_m)
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -318,7 +543,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     # ---- the other half of the headline metric: W1A16 GEMM throughput at prefill size (one BinaryDiff linear, 4096 tokens) ----
     gemm = None
-    if rank == 0 and not args.no_gemm:
+    if not args.no_gemm:  # every rank runs its own replica of the GEMM (no collective): aggregate = sum over the GPUs
         with torch.cuda.stream(stream):
             Mg, Ng, Kg = 4096, 4096, 4096
             lin = mods[0]["q_proj"]
@@ -332,9 +557,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 one(xg)
             g1.record(stream)
             torch.cuda.synchronize(dev)
-            us = g0.elapsed_time(g1) * 1e3 / 10
+            us_t = torch.tensor([g0.elapsed_time(g1) * 1e3 / 10], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(us_t, op=dist.ReduceOp.MAX)
+            us = us_t.item()
             tf = 4.0 * Mg * Ng * Kg / us / 1e6
-            gemm = {"shape": f"M={Mg} tokens x N={Ng} x K={Kg}, 1 delta (BinaryDiff prefill)", "us": us, "tflops": tf,
+            gemm = {"shape": f"M={Mg} tokens x N={Ng} x K={Kg}, 1 delta (BinaryDiff prefill), one replica per GPU", "us": us, "tflops": tf,
+                    "tflops_all_gpus": tf * world, "n_gpus": world,
                     "flops_counted": "4*M*N*K (base product + sign product, as the reference's notebook counts them)"}
 
     # ---- next row: the per-tenant dense leaves of the same decode step, each ONE native launch over the tenants ----
@@ -383,6 +612,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                       "step_extra_ms": (us_head + 65 * us_norm + us_emb) / 1e3,
                       "note": "not part of `value`: 1 lm_head + 65 RMSNorm + 1 embedding launches per decode step"}
             del heads, head, emb
+
+    # ---- BASELINE configs 4-5 mechanics on this box: strong scaling of tenant sharding, tensor-parallel 70B layers ----
+    strong = tp = triton_ref = None
+    if not args.no_extras:
+        strong = run_tenant_strong(torch, bd, dist, dev, rank, world, mods_all, stream, max(args.steps // 2, 5), args.warmup, barrier,
+                                   not args.no_group, gen)
+        torch.cuda.empty_cache()
+        tp = run_tp(torch, bd, dist, dev, rank, world, stream, max(args.steps, 10), args.warmup, barrier, args.tp_layers)
+        torch.cuda.empty_cache()
+    # ---- the reference's own GPU path (Triton) under the same harness: single-GPU runs only (it is not a scaling leg) ----
+    if rank == 0 and world == 1 and not args.no_triton_ref:
+        triton_ref = run_triton_reference(torch, mods, (x_h, x_a, x_m), y_static, stream, dev, max(args.steps // 5, 3))
 
     times = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -438,6 +679,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if leaves is not None:
             leaves["lm_head"]["frac"] = leaves["lm_head"]["gbps"] / hbm_peak
             line["tenant_leaves"] = leaves
+        if strong is not None:
+            line["tenant_strong_scaling"] = strong
+        if tp is not None:
+            line["tp"] = tp
+        if triton_ref is not None:
+            if "ms_per_step" in triton_ref:
+                triton_ref["ours_over_reference"] = triton_ref["ms_per_step"] / ms_step
+            line["triton_reference"] = triton_ref
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -454,6 +703,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill-size W1A16 GEMM measurement")
     ap.add_argument("--no-group", action="store_true", help="one launch per linear (no q/k/v and gate/up grouping)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and tensor-parallel legs")
+    ap.add_argument("--no-triton-ref", action="store_true", help="skip timing the reference's Triton path (single-GPU runs)")
+    ap.add_argument("--tp-layers", type=int, default=4, help="70B decoder layers per step of the tensor-parallel leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

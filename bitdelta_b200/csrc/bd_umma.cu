@@ -452,21 +452,39 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       // tenant tile: [16 rows x 64 B] as 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
       uint8_t* tile = xp + t * 1024 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
       uint32_t now_mask = 0;
-#pragma unroll
-      for (int b = 0; b < kD8Buckets; ++b) {
-        // byte q of the word goes to bucket b's rows iff element q is in bucket b: PRMT selector nibble q = q, else 4 (-> 0)
-        const uint32_t ne = bsel ^ (0x1111u * b);
-        const uint32_t nz = (ne | (ne >> 1) | (ne >> 2)) & 0x1111u;
-        const uint32_t sel = (0x3210u & ~(nz * 7u)) | (nz << 2);
-        const uint32_t v0 = __byte_perm(pw[0], 0, sel);  // first piece: non-zero iff the element is (NaN marker included)
-        const uint32_t live = v0 != 0 ? 1u : 0u;
-        now_mask |= live << b;
-        if (live | ((bucket_mask >> b) & 1u)) {
-          const uint32_t v[3] = {v0, __byte_perm(pw[1], 0, sel), __byte_perm(pw[2], 0, sel)};
+      const uint32_t b0 = bsel & 0xFu;
+      if (bsel == 0x1111u * b0) {
+        // Fast path (almost every word of real activations): the four elements share bucket b0, so the piece words go to
+        // that bucket's rows as they are; buckets that were live the last time are cleared.
+        now_mask = (pw[0] != 0 ? 1u : 0u) << b0;
+        uint32_t todo = now_mask | bucket_mask;
+        while (todo) {
+          const uint32_t b = 31u - __clz(todo);
+          todo &= ~(1u << b);
+          const bool mine = (b == b0);
 #pragma unroll
           for (int piece = 0; piece < 3; ++piece) {
-            const int rr = 3 * b + piece;
-            *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = v[piece];
+            const uint32_t rr = 3u * b + piece;
+            *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = mine ? pw[piece] : 0u;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < kD8Buckets; ++b) {
+          // byte q of the word goes to bucket b's rows iff element q is in bucket b: PRMT selector nibble q = q, else 4 (-> 0)
+          const uint32_t ne = bsel ^ (0x1111u * b);
+          const uint32_t nz = (ne | (ne >> 1) | (ne >> 2)) & 0x1111u;
+          const uint32_t sel = (0x3210u & ~(nz * 7u)) | (nz << 2);
+          const uint32_t v0 = __byte_perm(pw[0], 0, sel);  // first piece: non-zero iff the element is (NaN marker included)
+          const uint32_t live = v0 != 0 ? 1u : 0u;
+          now_mask |= live << b;
+          if (live | ((bucket_mask >> b) & 1u)) {
+            const uint32_t v[3] = {v0, __byte_perm(pw[1], 0, sel), __byte_perm(pw[2], 0, sel)};
+#pragma unroll
+            for (int piece = 0; piece < 3; ++piece) {
+              const int rr = 3 * b + piece;
+              *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = v[piece];
+            }
           }
         }
       }
@@ -610,7 +628,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // convert the signs; arrives with them on the A buffer's named barrier.
     Ring st, ab;
     // 8-bit path: live-bucket masks of this lane's (at most two) jobs, 5 bits per A buffer (see xperm_job)
-    unsigned long long bucket_state[2] = {0ull, 0ull};
+    unsigned long long bucket_state0 = 0ull, bucket_state1 = 0ull;
     uint32_t no_state = 0;
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
@@ -621,13 +639,15 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         if constexpr (DELTA8) {
           // at most T <= 10 tenants x 16 jobs: one or two jobs per lane, always the same ones
           const int sh = 5 * ab.idx;
-#pragma unroll
-          for (int ji = 0; ji < 2; ++ji) {
+#pragma unroll 1
+          for (int ji = 0; ji < 2; ++ji) {  // not unrolled: one copy of the job's code in the instruction cache
             const int job = (warp - kWarpXperm0) * 32 + lane + ji * kXpermWarps * 32;
             if (job < xjobs) {
-              uint32_t mask = (uint32_t)(bucket_state[ji] >> sh) & 31u;
+              unsigned long long stt = ji ? bucket_state1 : bucket_state0;
+              uint32_t mask = (uint32_t)(stt >> sh) & 31u;
               xperm_job(xsrc, xp, job, mask);
-              bucket_state[ji] = (bucket_state[ji] & ~(31ull << sh)) | ((unsigned long long)mask << sh);
+              stt = (stt & ~(31ull << sh)) | ((unsigned long long)mask << sh);
+              if (ji) bucket_state1 = stt; else bucket_state0 = stt;
             }
           }
         } else {
