@@ -348,9 +348,10 @@ def run_tp(torch, bd, dist, dev, rank: int, world: int, stream, steps: int, warm
     of the fp32 partials after each row-parallel linear (2 per layer).  Times `tp_layers` layers per step (weights + signs
     per rank exceed L2), with and without the collectives, and checks layer 0 against the unsharded modules."""
     from bitdelta_b200.diff import _fused_forward, _fused_forward_grouped
-    from bitdelta_b200.parallel import TensorParallelDiffLinear, split_column_parallel, split_row_parallel
+    from bitdelta_b200.parallel import PeerExchange, TensorParallelDiffLinear, split_column_parallel, split_row_parallel
 
     T = TP_TENANTS
+    exchange = PeerExchange(T * 8192) if world > 1 else None
     gen = torch.Generator(device=dev).manual_seed(777)  # same seed on every rank: identical full tensors, sharded locally
     layers, check = [], None
     for li in range(tp_layers):
@@ -372,23 +373,25 @@ def run_tp(torch, bd, dist, dev, rank: int, world: int, stream, steps: int, warm
     x_a = x_a_full[..., rank * 8192 // world:(rank + 1) * 8192 // world].contiguous()
     x_m = x_m_full[..., rank * 28672 // world:(rank + 1) * 28672 // world].contiguous()
 
+    torch.cuda.synchronize(dev)  # the operands were generated on the default stream; the legs below run on `stream`
+
     def col(layer, names, x):
         ms_ = [layer[nm] for nm in names]
         return _fused_forward_grouped(x, [m.weight for m in ms_], [m.mask for m in ms_], [m.coeff for m in ms_], T, "auto", static_operands=True)
 
-    def step(reduce: bool):
+    def row(mod, x, how):
+        if how == "none":  # the shard's own work only: fp32 partial sums rounded locally, no exchange
+            return _fused_forward(x, mod.weight, mod.mask, mod.coeff, T, "auto", static_operands=True, out_fp32=True).to(torch.bfloat16)
+        mod.exchange = exchange if how == "peer" else None  # "peer": bd_tp_allreduce over NVLink peer memory; "nccl": dist.all_reduce
+        return mod(x)
+
+    def step(how: str):
         y = None
         for layer in layers:
             col(layer, ("q_proj", "k_proj", "v_proj"), x_h)
-            if reduce:
-                layer["o_proj"](x_a)
-            else:
-                _fused_forward(x_a, layer["o_proj"].weight, layer["o_proj"].mask, layer["o_proj"].coeff, T, "auto", static_operands=True, out_fp32=True).to(torch.bfloat16)
+            row(layer["o_proj"], x_a, how)
             col(layer, ("gate_proj", "up_proj"), x_h)
-            if reduce:
-                y = layer["down_proj"](x_m)
-            else:
-                y = _fused_forward(x_m, layer["down_proj"].weight, layer["down_proj"].mask, layer["down_proj"].coeff, T, "auto", static_operands=True, out_fp32=True).to(torch.bfloat16)
+            y = row(layer["down_proj"], x_m, how)
         return y
 
     with torch.cuda.stream(stream):
@@ -399,31 +402,45 @@ def run_tp(torch, bd, dist, dev, rank: int, world: int, stream, steps: int, warm
             lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False, device=dev, dtype=torch.bfloat16)
             lin.weight.data = w
             y_full = bd.DiffCompressModule(lin, masks, coeffs)(xf)
-            y_tp = layers[0][name](xs)
-            torch.cuda.synchronize(dev)
-            parity[name] = {"mean_rel": ((y_tp.float() - y_full.float()).abs().mean() / y_full.float().abs().mean()).item(),
-                            "bit_equal_frac": (y_tp == y_full).float().mean().item()}
+            parity[name] = {}
+            for how in (("peer", "nccl") if world > 1 else ("nccl",)):
+                y_tp = row(layers[0][name], xs, how)
+                torch.cuda.synchronize(dev)
+                parity[name]["tp1" if world == 1 else how] = {
+                    "mean_rel": ((y_tp.float() - y_full.float()).abs().mean() / y_full.float().abs().mean()).item(),
+                    "bit_equal_frac": (y_tp == y_full).float().mean().item()}
         check = None
         torch.cuda.empty_cache()
-        step(True); step(False)
-        torch.cuda.synchronize(dev)
-        ms_with, _ = graph_time_ms(torch, lambda: step(True), stream, dev, steps, warmup, barrier)
-        ms_without, _ = graph_time_ms(torch, lambda: step(False), stream, dev, steps, warmup, barrier)
-    t = torch.tensor([ms_with, ms_without], device=dev, dtype=torch.float64)
+        hows = ["peer", "nccl", "none"] if world > 1 else ["none"]
+        ms = {}
+        for how in hows:
+            step(how)
+            torch.cuda.synchronize(dev)
+            ms[how], _ = graph_time_ms(torch, lambda: step(how), stream, dev, steps, warmup, barrier)
+    t = torch.tensor([ms[h] for h in hows], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_with, ms_without = t[0].item(), t[1].item()
+    ms = {h: t[i].item() for i, h in enumerate(hows)}
     per_rank_bytes = sum(2 * n * k + T * n * k // 8 for _, n, k, _ in LLAMA70B_LINEARS) // world
-    us_layer = ms_with * 1e3 / tp_layers
-    return {
+    best = "peer" if world > 1 else "none"
+    us_layer = ms[best] * 1e3 / tp_layers
+    out = {
         "workload": f"Llama-2-70B + {T} deltas decoder layers, tensor-parallel x{world}: column-parallel q/k/v (one launch) and gate/up (one launch), row-parallel o and down, {T} tenants x 1 token",
-        "layers_per_step": tp_layers, "us_per_layer": us_layer, "us_per_layer_without_collectives": ms_without * 1e3 / tp_layers,
-        "allreduce_us_each": (ms_with - ms_without) * 1e3 / (2 * tp_layers), "allreduces_per_layer": 2 if world > 1 else 0,
-        "collective_share_of_layer": (ms_with - ms_without) / ms_with if world > 1 else 0.0,
-        "collective": "NCCL all-reduce of the kernel's fp32 partial sums [8, 8192], one rounding after the sum" if world > 1 else "none (tp = 1)",
+        "layers_per_step": tp_layers, "us_per_layer": us_layer, "us_per_layer_without_exchange": ms["none"] * 1e3 / tp_layers,
+        "exchanges_per_layer": 2 if world > 1 else 0,
+        "collective": ("bd_tp_allreduce: one kernel over NVLink peer memory (push fp32 partials [8, 8192] to every rank, flag, sum in rank order, round once)"
+                       if world > 1 else "none (tp = 1)"),
         "tokens_s_80_layers": T / (us_layer * 80 * 1e-6), "per_rank_bytes_per_layer": per_rank_bytes,
-        "hbm_gbps_per_rank": per_rank_bytes / (us_layer * 1e-6) / 1e9, "parity_vs_unsharded": parity,
+        "hbm_gbps_per_rank": per_rank_bytes / (us_layer * 1e-6) / 1e9, "hbm_frac_per_rank": per_rank_bytes / (us_layer * 1e-6) / 1e9 / measured_peaks()[0],
+        "parity_vs_unsharded": parity,
     }
+    if world > 1:
+        out["exchange_us_each"] = (ms["peer"] - ms["none"]) * 1e3 / (2 * tp_layers)
+        out["exchange_share_of_layer"] = (ms["peer"] - ms["none"]) / ms["peer"]
+        out["nccl_variant"] = {"us_per_layer": ms["nccl"] * 1e3 / tp_layers, "allreduce_us_each": (ms["nccl"] - ms["none"]) * 1e3 / (2 * tp_layers),
+                               "what": "same shards, dist.all_reduce (NCCL) of the fp32 partials + a rounding kernel"}
+        exchange.close()
+    return out
 
 
 def run_tenant_strong(torch, bd, dist, dev, rank, world, mods, stream, steps, warmup, barrier, grouped, gen):
@@ -437,6 +454,7 @@ def run_tenant_strong(torch, bd, dist, dev, rank, world, mods, stream, steps, wa
     x_h = torch.randn(t_local, 1, 4096, generator=gen, device=dev).bfloat16()
     x_a = torch.randn(t_local, 1, 4096, generator=gen, device=dev).bfloat16()
     x_m = torch.randn(t_local, 1, 14336, generator=gen, device=dev).bfloat16()
+    torch.cuda.synchronize(dev)
     with torch.cuda.stream(stream):
         mistral_step(sub, x_h, x_a, x_m)
         torch.cuda.synchronize(dev)
@@ -485,8 +503,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         return mistral_step(mods, x_h, x_a, x_m)
 
     stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize(dev)  # the model was generated on the default stream
     with torch.cuda.stream(stream):
-        y_eager = step()  # also sizes the workspace on this stream
+        y_eager = step()  # also allocates the workspace of this stream
         torch.cuda.synchronize(dev)
         n0 = _lib.launch_count()
         graph = torch.cuda.CUDAGraph()

@@ -31,6 +31,7 @@ EXPORTS = [
     "bd_binary_bmm", "bd_binarydiff_fwd_batched", "bd_binarydiff_fwd_grouped",
     "bd_tenant_linear", "bd_tenant_rmsnorm", "bd_tenant_embed",
     "bd_workspace_bytes", "bd_select_kernel",
+    "bd_tp_buffer_bytes", "bd_tp_buffer_create", "bd_tp_buffer_open", "bd_tp_buffer_close", "bd_tp_allreduce",
 ]
 
 
@@ -65,6 +66,12 @@ def _load() -> ctypes.CDLL:
     lib.bd_workspace_bytes.argtypes = [i64, i64]
     lib.bd_workspace_bytes.restype = sz
     lib.bd_select_kernel.argtypes = [i32, i64, i64, i64, i64, i32]
+    lib.bd_tp_buffer_bytes.argtypes = [i64, i32]
+    lib.bd_tp_buffer_bytes.restype = sz
+    lib.bd_tp_buffer_create.argtypes = [sz, c.POINTER(vp), vp]
+    lib.bd_tp_buffer_open.argtypes = [vp, c.POINTER(vp)]
+    lib.bd_tp_buffer_close.argtypes = [vp, i32]
+    lib.bd_tp_allreduce.argtypes = [c.POINTER(vp), sz, i32, i32, vp, i64, vp, i32, vp]
     if BRINGUP:
         lib.bd_debug_set_trace.argtypes = [vp]
         lib.bd_debug_set_trace.restype = None

@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libbitdelta_b200.so")
 OUT_BRINGUP = os.path.join(PKG, "libbitdelta_b200_bringup.so")  # -DBD_BRINGUP: trace + A/B knobs, for tools/ only
-SOURCES = ["bd_api.cu", "bd_codec.cu", "bd_simt.cu", "bd_umma.cu", "bd_tenant.cu"]
+SOURCES = ["bd_api.cu", "bd_codec.cu", "bd_simt.cu", "bd_umma.cu", "bd_tenant.cu", "bd_tp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",

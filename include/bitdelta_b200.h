@@ -152,6 +152,27 @@ BD_API int bd_tenant_rmsnorm(const void* x, const void* const* w, void* y, int d
 BD_API int bd_tenant_embed(const int64_t* ids, const void* const* w, const int64_t* n_rows, void* y, int dtype, int64_t T, int64_t m,
                     int64_t H, void* stream);
 
+/* ---- e: tensor-parallel exchange for row-parallel BinaryDiff linears (BASELINE config 5) ------------------------
+ * The reference has no multi-GPU data path (its only multi-GPU artefact is accelerate layer placement,
+ * bitdelta/utils.py:82-101); a Megatron split of BinaryDiff.forward (bitdelta/diff.py:33-39) needs ONE sum over the ranks
+ * after each row-parallel linear (o_proj, down_proj).  bd_tp_allreduce does that sum in one kernel over NVLink peer memory
+ * instead of a library collective: every rank pushes its fp32 partial sums (the output of a forward launched with
+ * BD_FLAG_FP32_OUT) into all ranks' exchange buffers, signals, waits for the other ranks' signals and adds the slots in
+ * rank order -- deterministic, identical on every rank, one rounding to `dtype`.
+ *
+ * One exchange buffer per rank, created with bd_tp_buffer_create (cudaMalloc + zero fill; `ipc_handle64` receives the
+ * 64-byte cudaIpcMemHandle_t to send to the other ranks' processes) and mapped by them with bd_tp_buffer_open.
+ * bd_tp_buffer_bytes(max_elems, world) sizes it for sums of up to `max_elems` fp32 values.  bd_tp_allreduce takes the HOST
+ * array `bufs` of `world` device pointers (bufs[r] = rank r's buffer as mapped in this process, bufs[rank] the local one),
+ * all ranks must call it the same number of times with the same `n` (a multiple of 4); the call is asynchronous on
+ * `stream` and CUDA-graph capturable (its epoch counter lives in the buffer). */
+BD_API size_t bd_tp_buffer_bytes(int64_t max_elems, int world);
+BD_API int bd_tp_buffer_create(size_t bytes, void** dev_ptr, void* ipc_handle64);
+BD_API int bd_tp_buffer_open(const void* ipc_handle64, void** dev_ptr);
+BD_API int bd_tp_buffer_close(void* dev_ptr, int opened_from_handle);
+BD_API int bd_tp_allreduce(void* const* bufs, size_t buffer_bytes, int rank, int world, const float* partial, int64_t n, void* y,
+                           int dtype, void* stream);
+
 /* Upper bound of the workspace any forward of at most `max_rows` = T*m rows and `max_n` outputs needs on the
  * current device. */
 BD_API size_t bd_workspace_bytes(int64_t max_rows, int64_t max_n);

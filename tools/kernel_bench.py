@@ -4,7 +4,8 @@ operand sets larger than L2, so the number is device time per launch without Pyt
 usage: kernel_bench.py [kernel] [T,m,K,N ...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("BD_BRINGUP_LIB", "1")  # the library with the trace and the A/B knobs (build.py --bringup)
+if os.environ.get("BD_DBG_FLAGS", "0") != "0":
+    os.environ.setdefault("BD_BRINGUP_LIB", "1")  # A/B knobs exist only in the bring-up library (build.py --bringup); plain timings use the release library
 import torch
 import bitdelta_b200 as bd
 from bitdelta_b200.diff import _fused_forward
@@ -12,7 +13,8 @@ from bitdelta_b200.diff import _fused_forward
 dev = torch.device("cuda:0")
 kernel = sys.argv[1] if len(sys.argv) > 1 else "auto"
 from bitdelta_b200 import _lib
-_lib.lib.bd_debug_set_flags(int(os.environ.get("BD_DBG_FLAGS", "0")), int(os.environ.get("BD_LOAD_GROUP", "1")))
+if _lib.BRINGUP:
+    _lib.lib.bd_debug_set_flags(int(os.environ.get("BD_DBG_FLAGS", "0")), int(os.environ.get("BD_LOAD_GROUP", "1")))
 shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [
     (6, 1, 4096, 4096), (6, 1, 4096, 1024), (6, 1, 4096, 14336), (6, 1, 14336, 4096),
     (1, 1, 4096, 4096), (1, 1, 4096, 14336), (1, 16, 4096, 4096), (1, 128, 4096, 4096), (3, 1, 4096, 14336)]
