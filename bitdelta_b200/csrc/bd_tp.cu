@@ -49,6 +49,12 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
 }
 
 __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a) {
+  // Programmatic dependent launch on both sides: this grid is scheduled while the row-parallel forward that produces
+  // `partial` is still running (it needs no shared memory and few registers, so it co-resides) and blocks here until that
+  // forward has completed and flushed; the NEXT forward of the stream may start its prologue and prefetch its static
+  // weight / sign tiles while the exchange is in flight (its activation loads wait for this grid to complete).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   char* mine = a.bufs[a.rank];
   unsigned* hdr = reinterpret_cast<unsigned*>(mine);
   __shared__ unsigned s_epoch;
@@ -177,7 +183,16 @@ extern "C" BD_API int bd_tp_allreduce(void* const* bufs, size_t buffer_bytes, in
   // one float4 per thread up to 64 CTAs (all co-resident: the CTAs of a rank wait for flags that only peers can set)
   int64_t ctas = (n / 4 + kTpThreads - 1) / kTpThreads;
   if (ctas > 64) ctas = 64;
-  tp_allreduce_kernel<<<(unsigned)ctas, kTpThreads, 0, (cudaStream_t)stream>>>(a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kTpThreads);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see the kernel's griddepcontrol use
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BD_CUDA_OK(cudaLaunchKernelEx(&cfg, tp_allreduce_kernel, a));
   count_launch();
   return check_launch("tp_allreduce_kernel");
 }

@@ -80,3 +80,115 @@ def streaming_generator(model, tokenizers: Sequence, input_ids, attention_mask, 
                 resp = resp.split("<|")[0] + "</s>"
             response.append((resp, "continue"))
         yield json.dumps({"response": response}) + "\n\n"
+
+
+class GraphedDecoder:
+    """The decode step of ``greedy_steps`` as ONE CUDA graph over a static KV cache.
+
+    The reference re-enters Python for every token of every layer (demo_backend.py:231-243: ``model(...)`` with a growing
+    ``past_key_values`` and a re-concatenated attention mask).  Here the prefill runs eagerly into a ``StaticCache`` of
+    ``max_cache_len`` positions and every following step -- embedding, all decoder layers (fused BinaryDiff launches,
+    per-tenant norms), the per-tenant lm_heads, the greedy argmax and the bookkeeping for the next step -- is one graph
+    replay on static buffers:
+
+        tok [T,1]        the token fed to the step (the previous step's argmax)
+        mask [T,L]       1 for every cache position a row may attend to (left-padded prompt, generated tokens)
+        cache_pos [1]    the cache slot the step writes
+        pos_ids [T,1]    the row's rotary position
+
+    Batch row t is tenant t, as everywhere else.  Results are identical to the eager loop (``greedy_decode``): same
+    modules, same kernels, only the launch mechanism differs.
+    """
+
+    def __init__(self, model, max_cache_len: int):
+        from transformers import StaticCache
+
+        self.model = model
+        self.max_cache_len = int(max_cache_len)
+        self.cache = StaticCache(config=model.config, max_cache_len=self.max_cache_len)
+        self.graph = None
+        self.tok = self.mask = self.cache_pos = self.pos_ids = self.next_tok = None
+
+    def _forward_step(self):
+        out = self.model(self.tok, attention_mask=self.mask, past_key_values=self.cache, cache_position=self.cache_pos,
+                         position_ids=self.pos_ids, use_cache=True)
+        nxt = torch.argmax(out.logits[:, -1, :], dim=-1)
+        self.next_tok.copy_(nxt)
+        # state of the NEXT step, advanced on the device so that a replay is a whole step
+        self.tok.copy_(nxt[:, None])
+        self.cache_pos.add_(1)
+        self.pos_ids.add_(1)
+        self.mask.index_fill_(1, self.cache_pos, 1)
+
+    @torch.inference_mode()
+    def prefill(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        """Runs the prompt (left-padded like ``generate``) through the model into the static cache; returns the first
+        generated token [T] and arms the step state."""
+        T, P = input_ids.shape
+        assert P < self.max_cache_len, "prompt does not fit the static cache"
+        dev = input_ids.device
+        self.cache.reset()
+        pos = (attention_mask.long().cumsum(-1) - 1).clamp(min=0)
+        out = self.model(input_ids, attention_mask=attention_mask, past_key_values=self.cache,
+                         cache_position=torch.arange(P, device=dev), position_ids=pos, use_cache=True)
+        first = torch.argmax(out.logits[:, -1, :], dim=-1)
+        if self.tok is None:
+            self.tok = torch.empty((T, 1), dtype=torch.long, device=dev)
+            self.mask = torch.zeros((T, self.max_cache_len), dtype=attention_mask.dtype, device=dev)
+            self.cache_pos = torch.empty((1,), dtype=torch.long, device=dev)
+            self.pos_ids = torch.empty((T, 1), dtype=torch.long, device=dev)
+            self.next_tok = torch.empty((T,), dtype=torch.long, device=dev)
+        assert self.tok.shape[0] == T, "the graph is captured for a fixed number of tenants"
+        self.tok.copy_(first[:, None])
+        self.mask.zero_()
+        self.mask[:, :P] = attention_mask
+        self.mask[:, P] = 1
+        self.cache_pos.fill_(P)
+        self.pos_ids.copy_(pos[:, -1:] + 1)
+        self._steps_left = self.max_cache_len - P - 1
+        return first
+
+    @torch.inference_mode()
+    def capture(self, stream: Optional["torch.cuda.Stream"] = None):
+        """Captures one decode step.  Call after a ``prefill`` (the capture itself runs two warm-up steps and one captured
+        step on the armed state, then restores it).  Returns self."""
+        assert self.tok is not None, "prefill first: the static buffers are sized by the prompt batch"
+        saved = [t.clone() for t in (self.tok, self.mask, self.cache_pos, self.pos_ids)]
+        stream = stream or torch.cuda.Stream(device=self.tok.device)
+        stream.wait_stream(torch.cuda.current_stream(self.tok.device))
+        with torch.cuda.stream(stream):
+            for _ in range(2):  # warm-up on the capture stream: workspaces, lazily created buffers, cuBLAS handles
+                self._forward_step()
+            stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=stream):
+                self._forward_step()
+        torch.cuda.current_stream(self.tok.device).wait_stream(stream)
+        # the warm-up / capture steps wrote cache slots past the prompt; they are overwritten before they are ever attended to
+        for t, s in zip((self.tok, self.mask, self.cache_pos, self.pos_ids), saved):
+            t.copy_(s)
+        return self
+
+    @torch.inference_mode()
+    def step(self) -> torch.Tensor:
+        """One decode step for every tenant: returns the [T] tokens it produced (a view of a static buffer -- clone to keep)."""
+        assert self._steps_left > 0, "static cache exhausted"
+        self._steps_left -= 1
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._forward_step()
+        return self.next_tok
+
+    @torch.inference_mode()
+    def decode(self, input_ids, attention_mask, max_new_tokens: int, use_graph: bool = True) -> torch.Tensor:
+        """Greedy tokens [T, max_new_tokens] (prefill + graph replays), the graphed counterpart of ``greedy_decode``.
+        ``use_graph=False`` runs the same fixed-shape steps eagerly (what a CPU model always does)."""
+        cols = [self.prefill(input_ids, attention_mask).clone()]
+        if not use_graph:
+            self.graph = None
+        elif self.graph is None and input_ids.is_cuda:
+            self.capture()
+        for _ in range(max_new_tokens - 1):
+            cols.append(self.step().clone())
+        return torch.stack(cols, dim=1)

@@ -141,17 +141,26 @@ class SiblingGroup:
         self._x = None  # keeps the activations alive while outputs are cached, so the key cannot be recycled
         self._outs = {}
 
-    def forward_for(self, who, x):
-        # inference tensors (torch.inference_mode, which the reference's decode loop uses) carry no version counter
-        ver = 0 if x.is_inference() else x._version
-        key = (x.data_ptr(), ver, tuple(x.shape), x.dtype, x.device)
+    def invalidate(self, *_):
+        """Drops cached outputs.  `fuse_sibling_projections` calls it from a forward pre-hook of the parent block, so every
+        forward of the block starts a new round whatever happened to the activation buffer in between (a static-buffer
+        decode loop under torch.inference_mode updates it in place, and inference tensors carry no version counter)."""
+        self._key, self._x, self._outs = None, None, {}
+
+    def forward_for(self, who, hidden_states):
+        # The key is built from the tensor the CALLER passed (all members receive the same object from the decoder layer),
+        # so a non-contiguous input is made contiguous once per round, not once per member.
+        x0 = hidden_states
+        ver = 0 if x0.is_inference() else x0._version  # inference tensors have no version counter: see invalidate()
+        key = (x0.data_ptr(), ver, tuple(x0.shape), tuple(x0.stride()), x0.dtype, x0.device)
         if self._key != key or id(who) not in self._outs:
             T = who.mask.shape[0]
+            x = x0.contiguous()
             static = all(m.module.weight.is_contiguous() for m in self.members)  # a fresh copy is still queued on the stream
             ws = [m.module.weight if m.module.weight.is_contiguous() else m.module.weight.contiguous() for m in self.members]
             ys = _fused_forward_grouped(x, ws, [m.mask for m in self.members], [m.coeff for m in self.members], T, who.kernel,
                                         static_operands=static)
-            self._key, self._x = key, x
+            self._key, self._x = key, x0
             self._outs = {id(m): y for m, y in zip(self.members, ys)}
         y = self._outs.pop(id(who))
         if not self._outs:
@@ -181,7 +190,8 @@ def fuse_sibling_projections(model):
         for names in (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")):
             mods = [kids.get(nm) for nm in names]
             if all(isinstance(mm, DiffCompressModule) for mm in mods) and getattr(mods[0], "_group", None) is None:
-                group_projections(mods)
+                g = group_projections(mods)
+                g._hook = parent.register_forward_pre_hook(g.invalidate)  # a new round with every forward of the block
                 n += 1
     return n
 
@@ -202,9 +212,9 @@ class DiffCompressModule(nn.Module):
         # hidden_states: (T, seq, K)
         T = self.mask.shape[0]
         assert hidden_states.dim() == 3 and hidden_states.shape[0] == T, "Incompatible batch dimensions"
+        if self._group is not None and hidden_states.is_cuda:
+            return self._group.forward_for(self, hidden_states)
         x = hidden_states.contiguous()
-        if self._group is not None and x.is_cuda:
-            return self._group.forward_for(self, x)
         w = self.module.weight
         static = w.is_contiguous()  # module-owned buffers; a fresh .contiguous() copy is still queued on the stream
         if not static:
@@ -271,6 +281,10 @@ def unregister_diff_compress(model):
         if isinstance(mod, DataParallelModule):
             mod.module.weight.data = mod.original_weight
         elif isinstance(mod, DiffCompressModule):
+            hook = getattr(mod._group, "_hook", None) if mod._group is not None else None
+            if hook is not None:  # the parent block's round-invalidation hook of fuse_sibling_projections
+                hook.remove()
+                mod._group._hook = None
             mod._group = None
         else:
             continue

@@ -259,7 +259,8 @@ def load_diff(model, diff_dir):
     the parameter (cast to the model's dtype); an ``.A``/``.B`` LoRA pair adds ``(A@B).T``.  The config's vocabulary size
     follows the (possibly replaced) lm_head."""
     where = model.device
-    stored = torch.load(diff_dir, weights_only=False)
+    # diff.pt is a flat dict of tensors and Parameters (often downloaded from third parties): the safe unpickler is enough
+    stored = torch.load(diff_dir, map_location="cpu", weights_only=True)
 
     def fetch(key):
         return stored[key].to(where)

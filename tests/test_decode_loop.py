@@ -81,3 +81,18 @@ def test_streaming_generator_ndjson_contract(tiny):
         want_b = " ".join(f"b{int(t)}" for t in full[1, : i + 1])
         assert resp[1] == [want_b + ("</s>" if i >= 1 else ""), "continue"]
         assert resp[2][1] == "continue"
+
+
+def test_static_cache_decoder_matches_hf_generate(tiny):
+    """GraphedDecoder without a graph (CPU): prefill into a StaticCache, then fixed-shape steps whose bookkeeping (token,
+    cache slot, rotary position, attention mask) advances in place -- the same tokens as HF's greedy generate."""
+    from bitdelta_b200.decode import GraphedDecoder
+
+    model, ids, mask = tiny
+    n = 12
+    ref = model.generate(ids, attention_mask=mask, max_new_tokens=n, do_sample=False, pad_token_id=0, eos_token_id=None)[:, ids.shape[1]:]
+    dec = GraphedDecoder(model, max_cache_len=40)
+    assert torch.equal(dec.decode(ids, mask, n), ref)
+    assert torch.equal(dec.decode(ids, mask, n), ref)  # the cache and the step state are re-armed by every prefill
+    with pytest.raises(AssertionError):
+        GraphedDecoder(model, max_cache_len=ids.shape[1]).prefill(ids, mask)
