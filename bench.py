@@ -443,6 +443,108 @@ def run_tp(torch, bd, dist, dev, rank: int, world: int, stream, steps: int, warm
     return out
 
 
+def run_model_step(torch, bd, dev, steps: int, warmup: int, prompt_len: int = 64, max_cache_len: int = 512):
+    """SURVEY.md 8 row f-3 next to the headline: a WHOLE decode step of a random-init Mistral-7B served to 6 tenants through the
+    reference's registration surface (register_diff_compress: DiffCompressModule projections + DataParallelModule embedding /
+    norms / lm_heads with the demo's ragged vocabularies, fuse_sibling_projections) -- HF attention (SDPA over a static KV
+    cache), RoPE, residuals, SiLU, our fused linears and per-tenant leaves, greedy argmax -- captured as ONE CUDA graph
+    (bitdelta_b200.decode.GraphedDecoder; the reference's loop is demo/demo_backend.py:190-258)."""
+    import gc
+
+    from transformers import MistralConfig, MistralForCausalLM
+
+    from bitdelta_b200 import _lib
+    from bitdelta_b200 import demo_backend as db
+    from bitdelta_b200.decode import GraphedDecoder
+
+    vocab = (32000, 32000, 32002, 32002, 32002, 32002)  # the six demo tenants (SURVEY 8d config 3)
+    cfg = MistralConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=LAYERS, num_attention_heads=32, num_key_value_heads=8,
+                        vocab_size=vocab[0], max_position_embeddings=4096, sliding_window=None, tie_word_embeddings=False)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev):
+            model = MistralForCausalLM(cfg).eval()
+    finally:
+        torch.set_default_dtype(old)
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    sites = [(f"model.layers.{i}.{blk}.{name}", n, k) for i in range(LAYERS)
+             for blk, names in (("self_attn", ("q_proj", "k_proj", "v_proj", "o_proj")), ("mlp", ("gate_proj", "up_proj", "down_proj")))
+             for name in names for nm, n, k in MISTRAL_LINEARS if nm == name]
+    ckpts = []
+    for t in range(TENANTS):
+        ck = {}
+        for path, n, k in sites:
+            ck[path + ".mask"] = torch.randint(-(2**31), 2**31 - 1, (k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            ck[path + ".coeff"] = (torch.rand((), generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
+        ck["model.embed_tokens.weight"] = (torch.randn(vocab[t], 4096, generator=gen, device=dev) * 0.02).bfloat16()
+        ck["lm_head.weight"] = (torch.randn(vocab[t], 4096, generator=gen, device=dev) * 0.02).bfloat16()
+        for i in range(LAYERS):
+            for nm in ("input_layernorm", "post_attention_layernorm"):
+                ck[f"model.layers.{i}.{nm}.weight"] = (1.0 + 0.05 * torch.randn(4096, generator=gen, device=dev)).bfloat16()
+        ck["model.norm.weight"] = (1.0 + 0.05 * torch.randn(4096, generator=gen, device=dev)).bfloat16()
+        ckpts.append(ck)
+    db.cached_modules.clear()
+    out = None
+    try:
+        db.register_diff_compress(model, ckpts)
+        groups = db.fuse_sibling_projections(model)
+        ids = torch.randint(1, 32000, (TENANTS, prompt_len), generator=gen, device=dev)
+        am = torch.ones_like(ids)
+        am[1, :7] = 0  # left padding, like the reference's prompt batching
+        am[4, :19] = 0
+        ids = ids * am
+        torch.cuda.synchronize(dev)
+        dec = GraphedDecoder(model, max_cache_len=max_cache_len)
+        t0 = time.perf_counter()
+        dec.prefill(ids, am)
+        torch.cuda.synchronize(dev)
+        prefill_ms = (time.perf_counter() - t0) * 1e3
+        # eager static-cache steps (Python re-enters every module, like the reference's loop does)
+        for _ in range(2):
+            dec.step()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            dec.step()
+        torch.cuda.synchronize(dev)
+        eager_ms = (time.perf_counter() - t0) * 1e3 / 5
+        eager_tokens = dec.step().clone()
+        dec.prefill(ids, am)
+        n0 = _lib.launch_count()
+        dec.capture()
+        ours_per_step = (_lib.launch_count() - n0) // 3  # two warm-up steps + the captured one
+        for _ in range(7):
+            dec.step()
+        graph_tokens = dec.step().clone()  # the 8th step after the prefill, like eager_tokens above
+        for _ in range(warmup):
+            dec.step()
+        torch.cuda.synchronize(dev)
+        s = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(steps):
+            dec.step()
+        e1.record(s)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        out = {"ms_per_step": ms, "tokens_s": TENANTS / (ms * 1e-3), "steps": steps,
+               "what": "whole decode step of HF MistralForCausalLM (random init, 32 layers) for 6 tenants as one CUDA graph: embedding, RMSNorms, "
+                       "SDPA attention over a static KV cache, RoPE, residuals, SiLU, 224 BinaryDiff linears (fused launches), 6 ragged lm_heads, argmax",
+               "prompt_len": prompt_len, "kv_positions": max_cache_len, "vocab": list(vocab), "sibling_groups": groups,
+               "bitdelta_kernels_per_step": ours_per_step, "eager_static_cache_ms_per_step": eager_ms, "prefill_ms_eager": prefill_ms,
+               "graph_equals_eager_tokens": bool(torch.equal(eager_tokens, graph_tokens))}
+    except Exception as e:
+        out = {"unavailable": f"{type(e).__name__}: {e}"[:400]}
+    finally:
+        db.unregister_diff_compress(model)
+        db.cached_modules.clear()
+        del model, ckpts
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_tenant_strong(torch, bd, dist, dev, rank, world, mods, stream, steps, warmup, barrier, grouped, gen):
     """Strong scaling of tenant sharding: a FIXED set of 8 tenants split over the ranks (8 / world each), every rank still
     streaming its whole W_base replica -- the sub-linear curve SURVEY.md 8e predicts (per-GPU bytes 2NK + (T/G) NK/8)."""
@@ -643,6 +745,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- the reference's own GPU path (Triton) under the same harness: single-GPU runs only (it is not a scaling leg) ----
     if rank == 0 and world == 1 and not args.no_triton_ref:
         triton_ref = run_triton_reference(torch, mods, (x_h, x_a, x_m), y_static, stream, dev, max(args.steps // 5, 3))
+    model_step = None
+    if rank == 0 and world == 1 and not args.no_model_step:
+        model_step = run_model_step(torch, bd, dev, max(args.steps, 20), args.warmup)
 
     times = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -702,6 +807,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             line["tenant_strong_scaling"] = strong
         if tp is not None:
             line["tp"] = tp
+        if model_step is not None:
+            line["model_step"] = model_step
         if triton_ref is not None:
             if "ms_per_step" in triton_ref:
                 triton_ref["ours_over_reference"] = triton_ref["ms_per_step"] / ms_step
@@ -723,6 +830,7 @@ def main():
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill-size W1A16 GEMM measurement")
     ap.add_argument("--no-group", action="store_true", help="one launch per linear (no q/k/v and gate/up grouping)")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and tensor-parallel legs")
+    ap.add_argument("--no-model-step", action="store_true", help="skip the whole-model decode step leg (single-GPU runs)")
     ap.add_argument("--no-triton-ref", action="store_true", help="skip timing the reference's Triton path (single-GPU runs)")
     ap.add_argument("--tp-layers", type=int, default=4, help="70B decoder layers per step of the tensor-parallel leg")
     args = ap.parse_args()

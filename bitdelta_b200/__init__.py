@@ -14,16 +14,17 @@ from .demo_backend import (
     DiffCompressModule,
     fuse_sibling_projections,
     group_projections,
+    load_checkpoints_stacked,
     register_diff_compress,
     unregister_diff_compress,
 )
 from .diff import BinaryDiff, compress_diff, fold_into, load_diff, save_diff, save_full_model
 from . import parallel  # noqa: F401
-from .decode import greedy_decode, greedy_steps, streaming_generator
+from .decode import GraphedDecoder, greedy_decode, greedy_steps, streaming_generator
 
 __all__ = [
     "pack", "unpack", "binary_matmul", "binary_bmm",
     "BinaryDiff", "compress_diff", "save_diff", "load_diff", "save_full_model", "fold_into",
-    "DiffCompressModule", "DataParallelModule", "register_diff_compress", "unregister_diff_compress", "DiffCompress", "group_projections", "fuse_sibling_projections",
-    "greedy_steps", "greedy_decode", "streaming_generator",
+    "DiffCompressModule", "DataParallelModule", "register_diff_compress", "unregister_diff_compress", "DiffCompress", "group_projections", "fuse_sibling_projections", "load_checkpoints_stacked",
+    "greedy_steps", "greedy_decode", "streaming_generator", "GraphedDecoder",
 ]

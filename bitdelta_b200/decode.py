@@ -153,7 +153,14 @@ class GraphedDecoder:
         """Captures one decode step.  Call after a ``prefill`` (the capture itself runs two warm-up steps and one captured
         step on the armed state, then restores it).  Returns self."""
         assert self.tok is not None, "prefill first: the static buffers are sized by the prompt batch"
-        saved = [t.clone() for t in (self.tok, self.mask, self.cache_pos, self.pos_ids)]
+        layers = list(getattr(self.cache, "layers", []))
+        assert not any(getattr(l, "is_sliding", False) for l in layers), \
+            "sliding-window cache layers keep their write position on the host: not capturable (build the config with sliding_window=None)"
+        # transformers' StaticLayer advances its own device-side write position (`cumulative_length`) with every update:
+        # the warm-up steps below move it, so it is part of the state to put back
+        state = [self.tok, self.mask, self.cache_pos, self.pos_ids]
+        state += [l.cumulative_length for l in layers if isinstance(getattr(l, "cumulative_length", None), torch.Tensor)]
+        saved = [t.clone() for t in state]
         stream = stream or torch.cuda.Stream(device=self.tok.device)
         stream.wait_stream(torch.cuda.current_stream(self.tok.device))
         with torch.cuda.stream(stream):
@@ -165,7 +172,7 @@ class GraphedDecoder:
                 self._forward_step()
         torch.cuda.current_stream(self.tok.device).wait_stream(stream)
         # the warm-up / capture steps wrote cache slots past the prompt; they are overwritten before they are ever attended to
-        for t, s in zip((self.tok, self.mask, self.cache_pos, self.pos_ids), saved):
+        for t, s in zip(state, saved):
             t.copy_(s)
         return self
 

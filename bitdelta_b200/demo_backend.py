@@ -254,6 +254,40 @@ def _stack_tenant_deltas(path, checkpoint_list):
     return masks, coeffs
 
 
+def load_checkpoints_stacked(paths, device, dtype=torch.float16):
+    """diff.pt files -> what ``register_diff_compress`` consumes, without the host-side detour of the reference's start-up
+    (demo_backend.py:26-35 loads every file to the CPU, moves each tensor to the GPU, and :131-141 then stacks the tenants'
+    masks on the device next to the per-tenant copies before popping them).
+
+    The files are memory-mapped (``torch.load(mmap=True, weights_only=True)``); every projection's sign words go with ONE
+    host-to-device copy per tenant straight into their slice of the final ``[T, K/32, N]`` tensor (the layout the fused
+    kernel reads), the scales into the ``[T]`` tensor, and both are published in ``cached_modules`` under the module path
+    exactly as ``register_diff_compress`` would have cached them.  Returns the checkpoint list (one dict per tenant) holding
+    only what is left: the tenants' full-precision leaves (``*.weight``) on ``device`` in ``dtype``.  Nothing else changes:
+    ``register_diff_compress(model, load_checkpoints_stacked(paths, device))``.
+    """
+    files = [torch.load(p, map_location="cpu", mmap=True, weights_only=True) for p in paths]
+    T = len(files)
+    out = [dict() for _ in range(T)]
+    for key in files[0]:
+        if key.endswith(".mask"):
+            path = key[: -len(".mask")]
+            first = files[0][key]
+            masks = torch.empty((T,) + tuple(first.shape), dtype=torch.int32, device=device)
+            for t, f in enumerate(files):
+                masks[t].copy_(f[key], non_blocking=True)
+            coeffs = torch.stack([f[f"{path}.coeff"].detach().reshape(()) for f in files]).to(device=device, dtype=dtype)
+            cached_modules[path] = (masks, coeffs)
+        elif key.endswith(".coeff"):
+            continue
+        else:
+            for t, f in enumerate(files):
+                out[t][key] = f[key].detach().to(device=device, dtype=dtype)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+    return out
+
+
 def register_diff_compress(model, checkpoint_list):
     """Wrap every leaf whose path appears in the tenants' checkpoints (reference :107-153).
 

@@ -238,3 +238,37 @@ def test_register_unregister_on_nested_hf_model(golden):
                 assert set(db.cached_modules) == {n for n, k in kinds.items() if k == "DiffCompressModule"}
     finally:
         db.cached_modules.clear()
+
+
+def test_load_checkpoints_stacked_equals_load_then_register(golden):
+    """f-1: the memory-mapped loader puts every tenant's sign words straight into the stacked [T, K/32, N] tensor and
+    publishes it in ``cached_modules``; registering from it builds exactly the modules the reference's load-to-CPU,
+    move, stack, pop sequence builds (demo_backend.py:26-35, :131-141)."""
+    from bitdelta_b200 import demo_backend as db
+
+    g, cfg, model = _tiny_models(golden)
+    path = os.path.join(os.path.dirname(__file__), "golden", "tiny_llama_diff.pt")
+    db.cached_modules.clear()
+    try:
+        ckpts = []
+        for _ in range(3):
+            d = torch.load(path, weights_only=False)
+            ckpts.append({k: (v.detach().to(torch.bfloat16) if v.is_floating_point() else v) for k, v in d.items()})
+        db.register_diff_compress(model, ckpts)
+        want = {n: (m.mask.clone(), m.coeff.clone()) for n, m in model.named_modules() if isinstance(m, db.DiffCompressModule)}
+        want_w = {n: [w.clone() for w in m.weight_list] for n, m in model.named_modules() if isinstance(m, db.DataParallelModule)}
+        db.unregister_diff_compress(model)
+        db.cached_modules.clear()
+        rest = db.load_checkpoints_stacked([path] * 3, "cpu", torch.bfloat16)
+        assert set(db.cached_modules) == set(want) and len(rest) == 3
+        assert not any(k.endswith((".mask", ".coeff")) for k in rest[0])
+        db.register_diff_compress(model, rest)
+        for n, m in model.named_modules():
+            if isinstance(m, db.DiffCompressModule):
+                assert torch.equal(m.mask, want[n][0]) and torch.equal(m.coeff, want[n][1]) and m.mask.is_contiguous()
+            elif isinstance(m, db.DataParallelModule):
+                assert all(torch.equal(a, b) for a, b in zip(m.weight_list, want_w[n]))
+        assert {n for n, m in model.named_modules() if isinstance(m, db.DiffCompressModule)} == set(want)
+        db.unregister_diff_compress(model)
+    finally:
+        db.cached_modules.clear()
