@@ -55,9 +55,11 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxRows = 128;  // rows (tokens) per launch
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 24;
-// 8-bit delta path: static exponent windows of the activation split (see xperm_job)
-constexpr int kD8Buckets = 5;
-constexpr int kD8ExpLo = 127 - 60;  // biased bf16 exponent of the lowest bucket's lower edge (2^-60)
+// 8-bit delta path: every activation row is scaled by a power of two taken from the largest exponent of the row inside this
+// CTA's K range, so that its three e5m2 pieces sit in e5m2's exponent window (see the row-scale pass and xperm_job)
+constexpr int kD8MaxTenants = 16;   // rows of s_rowexp (the TMEM budget allows 10)
+constexpr int kBarRowScale = 12;    // named barrier of the row-scale pass (unpack + permute warps)
+constexpr int kD8TopExp = 14;       // the row maximum is scaled to [2^14, 2^15): the first piece stays below e5m2's 57344
 
 // ---------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,6 +167,7 @@ struct UmmaMaps {
 };
 
 struct UmmaArgs {
+  const void* x;       // activations [rows, K] (the 8-bit path scans them for the row scales; everything else goes through TMA)
   const void* coeff;   // segment 0 (kept for the single-matrix case)
   int coeff_dtype;
   void* y;
@@ -326,6 +329,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   __shared__ uint32_t tmem_base_slot;
   __shared__ unsigned s_is_last;
   __shared__ int s_released;  // number of units the sync warp has released to the unpack group (release/acquire)
+  __shared__ int s_rowexp[kD8MaxTenants];  // 8-bit path: largest biased bf16 exponent of tenant t's row over this CTA's K range
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
@@ -376,6 +380,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     fence_barrier_init();
   }
   if (threadIdx.x == 0) s_released = 0;
+  if (DELTA8 && threadIdx.x < kD8MaxTenants) s_rowexp[threadIdx.x] = 0;
   __syncthreads();  // mbarriers initialised
   // The TMA producer needs nothing else: it starts requesting the first weight / sign stages right away, while the other
   // warps allocate tensor memory and zero the permuted-activation tiles and rendezvous without it.
@@ -399,40 +404,79 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   const uint32_t a_cols_per_buf = (uint32_t)a.T * a.a_cols_tenant;
   const uint32_t col_abuf0 = kTmemCols - a.n_abuf * a_cols_per_buf;
 
+  // ---- 8-bit path: row scales ----
+  // e5m2 has fp16's 5-bit exponent, bf16 has 8: before an activation is split into e5m2 pieces it is multiplied by
+  // 2^(kD8TopExp - emax_t), emax_t = the largest exponent of tenant t's row over the K blocks THIS CTA consumes (its unit run;
+  // the scale only has to be the same for everything one CTA accumulates -- partial sums leave the CTA descaled, in fp32).
+  // The row maximum then sits in [2^14, 2^15); three pieces (3 + 3 + 2 significant bits) hold every element down to
+  // 2^-23 of the row maximum exactly, and smaller ones to an absolute error below 2^-31 of the row maximum -- the order of
+  // the rounding error of the fp32 accumulation itself, whatever the magnitude or dynamic range of the row.  inf / NaN
+  // elements become NaN pieces (the row's outputs are NaN, like the reference's).
+  // The unpack and permute warps scan the rows (from L2: T x <= K values per CTA) while the first stages are in flight.
+  if constexpr (DELTA8) {
+    if (warp < kWarpSync) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are produced by the previous kernel of the stream
+      constexpr int kScanThreads = kWarpSync * 32;
+      const int nkb = min(u_end - u_begin, a.kblocks);    // K blocks kb0, kb0 + 1, ... (mod kblocks) of this CTA's run
+      const int chunks = nkb * (kBlockK / 8);             // 16-byte chunks (8 values) per row
+      const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x);
+      uint32_t mx[10];
+#pragma unroll
+      for (int t = 0; t < 10; ++t) mx[t] = 0u;
+      for (int ci = threadIdx.x; ci < chunks; ci += kScanThreads) {
+        int kb = kb0 + (ci >> 3);
+        if (kb >= a.kblocks) kb -= a.kblocks;
+        const int k = kb * kBlockK + (ci & 7) * 8;
+        if (k < a.K) {  // K % 8 == 0: a chunk is inside the row or outside it
+#pragma unroll
+          for (int t = 0; t < 10; ++t) {
+            if (t < a.T) {
+              const uint4 v = __ldcg(reinterpret_cast<const uint4*>(xg + (size_t)t * a.K + k));
+              // exponent fields of the two bf16 halves of a word, compared as packed unsigned 16-bit values
+              mx[t] = __vmaxu2(__vmaxu2(mx[t], v.x & 0x7F807F80u), __vmaxu2(v.y & 0x7F807F80u, __vmaxu2(v.z & 0x7F807F80u, v.w & 0x7F807F80u)));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 10; ++t) {
+        if (t < a.T) {
+          const uint32_t e = max(mx[t] & 0xFFFFu, mx[t] >> 16) >> 7;
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, e);
+          if (lane == 0 && wmax != 0u) atomicMax(&s_rowexp[t], (int)wmax);
+        }
+      }
+      named_bar_sync(kBarRowScale, kScanThreads);
+    }
+  }
+  // scale applied to tenant t's activations before the split, as the exponent field of a float: 2^(kD8TopExp - (emax - 127)),
+  // clamped to a normal number whose reciprocal is normal too
+  auto d8_scale_field = [&](int t) -> uint32_t { return (uint32_t)min(max(254 + kD8TopExp - s_rowexp[t], 1), 253); };
+
   // K-permuted copy of the activation rows for A buffer `b` (see the header comment): job = (row r, 16-byte output
   // chunk c of the 64-K block); out chunk c of a 32-group = x[4c..4c+3] interleaved with x[4c+16..4c+19]; source and
   // destination tiles use the 128-byte swizzle (chunk index XOR row % 8).
-  auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job, uint32_t& bucket_mask) {
+  auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job, uint32_t scale_field) {
     if constexpr (DELTA8) {
       // 8-bit delta path (one row per tenant).  job = (row r, 32-group g, c): one 32-bit output word per B-operand row,
       // holding K slots 4c..4c+3 of the group = activations k = c + 8q, q = 0..3 (the order the e4m3 sign registers are
       // built in).  Jobs are kept this small on purpose: a warp executes a job's instructions once however many lanes
       // are active, and the issue slots of the sub-partition this warp shares with two unpack warps are the scarce resource.
       //
-      // Every bf16 activation is represented EXACTLY by three e5m2 pieces p1 + p2 + p3 (round-to-nearest residual chain:
-      // 3 + 3 + 2 significant bits cover bf16's 8) of x * 2^-c_b, where b is one of kD8Buckets static exponent windows of 24
-      // binades: e5m2 holds the three pieces exactly while the scaled exponent stays in [-9, 14] (lowest piece bit >= 2^-16,
-      // p1 <= 2^15), so bucket b takes the activations with 2^(-60+24b) <= |x| < 2^(-36+24b) and the five buckets cover
-      // [2^-60, 2^60) -- whatever the scale of the row, with no data-dependent pre-pass.  Each (bucket, piece) is its own
-      // B-operand row (15 of the tenant's 16 accumulator columns); an element is zero in the rows of the other buckets.
-      // The epilogue adds sum_b 2^c_b * (d[3b] + d[3b+1] + d[3b+2]) in fp32.  |x| < 2^-60 degrades gradually (absolute error
-      // < 2^-76 per element); |x| >= 2^60, inf and NaN become NaN pieces: the result is NaN, never a silently clipped number.
-      // Stores: a bucket's three words are written only if the bucket holds a non-zero element now or did the last time this
-      // job wrote this A buffer's tile (bucket_mask, kept by the caller per (job, A buffer); the tiles start zeroed) --
-      // real activation blocks live in one or two adjacent buckets, so 3-6 of the 15 (bank-conflicting) stores remain.
+      // The activation, scaled by the row's power of two (see the row-scale pass), is split into three e5m2 pieces
+      // p1 + p2 + p3 by a round-to-nearest residual chain (3 + 3 + 2 significant bits cover bf16's 8); each piece is its own
+      // B-operand row (3 of the tenant's 8 accumulator columns) and the epilogue adds the three partial sums and undoes
+      // the scale in fp32.
       const int r = job >> 4, g = (job >> 3) & 1, c = job & 7;
       const uint8_t* src = xsrc + r * 128 + 2 * (c & 7);
+      const float scale = __uint_as_float(scale_field << 23);
       float f[4];
-      uint32_t bsel = 0, bad = 0;
+      uint32_t bad = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // element 32g + c + 8q lives in 16-byte chunk 4g + q (swizzled by the row)
         const uint32_t bits = *reinterpret_cast<const unsigned short*>(src + (((4 * g + q) ^ (r & 7)) << 4));
-        const int eb = (int)((bits >> 7) & 0xFFu);                      // biased exponent; bucket = floor((eb - 67) / 24)
-        const int b = min((max(eb - kD8ExpLo, 0) * 171) >> 12, kD8Buckets - 1);
-        bsel |= (uint32_t)b << (4 * q);
-        bad |= (eb >= kD8ExpLo + 24 * kD8Buckets ? 0xFFu : 0u) << (8 * q);
-        // x * 2^(51 - 24b): the bucket's lowest exponent lands on 2^-9
-        f[q] = __uint_as_float(bits << 16) * __uint_as_float((uint32_t)(127 + 51 - 24 * b) << 23);
+        bad |= ((bits & 0x7F80u) == 0x7F80u ? 0xFFu : 0u) << (8 * q);  // inf / NaN
+        f[q] = __uint_as_float(bits << 16) * scale;
       }
       uint32_t pw[3];
 #pragma unroll
@@ -447,48 +491,11 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           f[0] -= b01.x; f[1] -= b01.y; f[2] -= b23.x; f[3] -= b23.y;
         }
       }
-      pw[0] = (pw[0] & ~bad) | (0x7E7E7E7Eu & bad);  // out of range / non-finite: e5m2 NaN
-      const int t = r;                               // one row per tenant on this path
-      // tenant tile: [16 rows x 64 B] as 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
-      uint8_t* tile = xp + t * 1024 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
-      uint32_t now_mask = 0;
-      const uint32_t b0 = bsel & 0xFu;
-      if (bsel == 0x1111u * b0) {
-        // Fast path (almost every word of real activations): the four elements share bucket b0, so the piece words go to
-        // that bucket's rows as they are; buckets that were live the last time are cleared.
-        now_mask = (pw[0] != 0 ? 1u : 0u) << b0;
-        uint32_t todo = now_mask | bucket_mask;
-        while (todo) {
-          const uint32_t b = 31u - __clz(todo);
-          todo &= ~(1u << b);
-          const bool mine = (b == b0);
+      pw[0] = (pw[0] & ~bad) | (0x7E7E7E7Eu & bad);  // non-finite activation: e5m2 NaN
+      // tenant tile: [8 rows x 64 B] as four 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
+      uint8_t* tile = xp + r * 512 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
 #pragma unroll
-          for (int piece = 0; piece < 3; ++piece) {
-            const uint32_t rr = 3u * b + piece;
-            *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = mine ? pw[piece] : 0u;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < kD8Buckets; ++b) {
-          // byte q of the word goes to bucket b's rows iff element q is in bucket b: PRMT selector nibble q = q, else 4 (-> 0)
-          const uint32_t ne = bsel ^ (0x1111u * b);
-          const uint32_t nz = (ne | (ne >> 1) | (ne >> 2)) & 0x1111u;
-          const uint32_t sel = (0x3210u & ~(nz * 7u)) | (nz << 2);
-          const uint32_t v0 = __byte_perm(pw[0], 0, sel);  // first piece: non-zero iff the element is (NaN marker included)
-          const uint32_t live = v0 != 0 ? 1u : 0u;
-          now_mask |= live << b;
-          if (live | ((bucket_mask >> b) & 1u)) {
-            const uint32_t v[3] = {v0, __byte_perm(pw[1], 0, sel), __byte_perm(pw[2], 0, sel)};
-#pragma unroll
-            for (int piece = 0; piece < 3; ++piece) {
-              const int rr = 3 * b + piece;
-              *reinterpret_cast<uint32_t*>(tile + (rr >> 3) * 512 + (rr & 7) * 16) = v[piece];
-            }
-          }
-        }
-      }
-      bucket_mask = now_mask;
+      for (int piece = 0; piece < 3; ++piece) *reinterpret_cast<uint32_t*>(tile + piece * 16) = pw[piece];
       return;
     }
     const int r = job >> 3, c = job & 7;
@@ -563,7 +570,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // descriptor low words (address >> 4) of stage 0 / A buffer 0 and their strides
     const uint32_t w_lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4, stage_lo = a.stage_bytes >> 4;
     const uint32_t x_off_lo = a.off_x >> 4;
-    const uint32_t xp_lo0 = (smem_u32(smem + a.off_xp) & 0x3FFFFu) >> 4, xp_buf_lo = a.xp_buf_bytes >> 4, xp_t_lo = DELTA8 ? (1024u >> 4) : (uint32_t)a.mp * 8;
+    const uint32_t xp_lo0 = (smem_u32(smem + a.off_xp) & 0x3FFFFu) >> 4, xp_buf_lo = a.xp_buf_bytes >> 4, xp_t_lo = DELTA8 ? (512u >> 4) : (uint32_t)a.mp * 8;
     Ring st, ab;
     int kb = kb0;
 #pragma unroll 1
@@ -627,9 +634,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // Released per unit by the sync warp (shared-memory counter); permutes / splits the activations while the unpack warps
     // convert the signs; arrives with them on the A buffer's named barrier.
     Ring st, ab;
-    // 8-bit path: live-bucket masks of this lane's (at most two) jobs, 5 bits per A buffer (see xperm_job)
-    unsigned long long bucket_state0 = 0ull, bucket_state1 = 0ull;
-    uint32_t no_state = 0;
+    // 8-bit path: this lane's (at most two) jobs always belong to the same tenants: their scales are loop invariants
+    uint32_t sf0 = 0, sf1 = 0;
+    if constexpr (DELTA8) {
+      const int j0 = (warp - kWarpXperm0) * 32 + lane, j1 = j0 + kXpermWarps * 32;
+      if (j0 < xjobs) sf0 = d8_scale_field(j0 >> 4);
+      if (j1 < xjobs) sf1 = d8_scale_field(j1 >> 4);
+    }
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
       wait_released(&s_released, u - u_begin);
@@ -637,23 +648,16 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         const uint8_t* xsrc = smem + (size_t)st.idx * a.stage_bytes + a.off_x;
         uint8_t* xp = smem + a.off_xp + (size_t)ab.idx * a.xp_buf_bytes;
         if constexpr (DELTA8) {
-          // at most T <= 10 tenants x 16 jobs: one or two jobs per lane, always the same ones
-          const int sh = 5 * ab.idx;
+          // at most T <= 10 tenants x 16 jobs: one or two jobs per lane
 #pragma unroll 1
           for (int ji = 0; ji < 2; ++ji) {  // not unrolled: one copy of the job's code in the instruction cache
             const int job = (warp - kWarpXperm0) * 32 + lane + ji * kXpermWarps * 32;
-            if (job < xjobs) {
-              unsigned long long stt = ji ? bucket_state1 : bucket_state0;
-              uint32_t mask = (uint32_t)(stt >> sh) & 31u;
-              xperm_job(xsrc, xp, job, mask);
-              stt = (stt & ~(31ull << sh)) | ((unsigned long long)mask << sh);
-              if (ji) bucket_state1 = stt; else bucket_state0 = stt;
-            }
+            if (job < xjobs) xperm_job(xsrc, xp, job, ji ? sf1 : sf0);
           }
         } else {
           // small row counts: these three warps do all of it; prefill-size row counts: shared with the 8 unpack warps
           const int j0 = xperm_shared ? kUnpackWarps * 32 : 0, jstride = xperm_shared ? (kUnpackWarps + kXpermWarps) * 32 : kXpermWarps * 32;
-          for (int job = j0 + (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += jstride) xperm_job(xsrc, xp, job, no_state);
+          for (int job = j0 + (warp - kWarpXperm0) * 32 + lane; job < xjobs; job += jstride) xperm_job(xsrc, xp, job, 0u);
         }
         fence_proxy_async();
       }
@@ -787,7 +791,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const uint8_t* sp = smem + (size_t)st_i.idx * a.stage_bytes;
           if (!NATK && xperm_shared) {  // large row counts: the unpack warps share the activation permutation
             uint8_t* xp = smem + a.off_xp + (size_t)ab_i.idx * a.xp_buf_bytes;
-            for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) { uint32_t none = 0; xperm_job(sp + a.off_x, xp, job, none); }
+            for (int job = ut; job < xjobs; job += (kUnpackWarps + kXpermWarps) * 32) xperm_job(sp + a.off_x, xp, job, 0u);
           }
           unpack_unit(sp, ab_i.idx, grp, 2);
           st_i.advance(a.stages);
@@ -842,21 +846,15 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
 
         if constexpr (DELTA8) {
-          // delta accumulator: 16 columns per tenant (one row per tenant), column 3b+p = piece p of exponent bucket b,
-          // scaled by 2^(51-24b); the two warps of a quadrant take alternate tenants
+          // delta accumulator: 8 columns per tenant (one row per tenant), columns 0..2 = the three pieces of the scaled
+          // activation; the two warps of a quadrant take alternate tenants
           for (int t = grp; t < a.T; t += 2) {
             const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
-            float d0[8], d1[8], bv = 0.f;
-            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16, d0);
-            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 16 + 8, d1);
+            float d0[8], bv = 0.f;
+            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 8, d0);
             if (HAS_BASE) bv = tmem_ld1(tmem_base + lane_addr + col_dbase + t);
             tc_wait_ld();
-            // small buckets first; each term is exact in fp32 up to the accumulator's own rounding
-            float dsum = (d0[0] + d0[1] + d0[2]) * 0x1p-51f;
-            dsum = fmaf(d0[3] + d0[4] + d0[5], 0x1p-27f, dsum);
-            dsum = fmaf(d0[6] + d0[7] + d1[0], 0x1p-3f, dsum);
-            dsum = fmaf(d1[1] + d1[2] + d1[3], 0x1p21f, dsum);
-            dsum = fmaf(d1[4] + d1[5] + d1[6], 0x1p45f, dsum);
+            const float dsum = (d0[0] + d0[1] + d0[2]) * __uint_as_float((254u - d8_scale_field(t)) << 23);  // undo the row scale
             const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
             if (full_k) {
               if (n < seg_n) store_y(y, (int64_t)t * seg_n + n, v, a.fp32_out);
@@ -1028,7 +1026,7 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
   if (N % 4 != 0) { p.why = "N must be a multiple of 4 (TMA row pitch of the sign words)"; return p; }
   if (K % 32 != 0) { p.why = "K must be a multiple of 32"; return p; }
   if ((N + kTileN - 1) / kTileN > (int64_t)(kWsCounterBytes / sizeof(unsigned))) { p.why = "too many N tiles"; return p; }
-  p.mp = d8 ? 16 : (int)((m + 15) / 16 * 16);  // delta accumulator columns per tenant (8-bit path: 5 buckets x 3 pieces of the one row)
+  p.mp = d8 ? 8 : (int)((m + 15) / 16 * 16);  // delta accumulator columns per tenant (8-bit path: the 3 pieces of the one row)
   p.a_cols_tenant = d8 ? kBlockK / 4 : kBlockK / 2;
   p.ntb = (int)((rows + 15) / 16 * 16);
   const int64_t a_cols_one = T * p.a_cols_tenant;
@@ -1037,7 +1035,7 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
   if (nbuf > kMaxABuf) nbuf = kMaxABuf;
   // the K-permuted activation tiles (one set per A buffer) live in shared memory: keep them under 48 KiB
   p.natk = !d8 && T == 1;  // one tenant, 16-bit signs: natural K order, no permuted activation copy
-  const int64_t xp_one = p.natk ? 1024 : (d8 ? T * 1024 : T * p.mp * 128);
+  const int64_t xp_one = p.natk ? 1024 : (d8 ? T * 512 : T * p.mp * 128);
   while (nbuf > 2 && nbuf * xp_one > 48 * 1024) --nbuf;
   p.n_abuf = (int)nbuf;
   const uint32_t w_bytes = has_base ? kTileN * kBlockK * 2 : 0;
@@ -1178,7 +1176,7 @@ static int launch_one(const FwdProblem& p) {
 
   const int64_t rows = T * m;
   UmmaArgs a{};
-  a.coeff = p.coeff; a.coeff_dtype = p.coeff_dtype; a.y = p.y;
+  a.x = p.x; a.coeff = p.coeff; a.coeff_dtype = p.coeff_dtype; a.y = p.y;
   a.T = (int)T; a.m = (int)m; a.rows = (int)rows; a.inv_m = (uint32_t)((65536 + m - 1) / m); a.mp = plan.mp; a.ntb = plan.ntb;
   a.K = (int)p.K; a.N = (int)p.N;
   a.kblocks = (int)((p.K + kBlockK - 1) / kBlockK);

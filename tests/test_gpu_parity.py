@@ -801,10 +801,11 @@ def test_cuda_graph_capture_of_the_fused_forward():
 
 # ------------------------------------------------------------------------------------------------ activation range
 # The decode launches of the tcgen05 kernel (bf16, one row per tenant) feed the delta product from 8-bit operands: the
-# activations are split exactly into e5m2 pieces inside static exponent buckets (bd_umma.cu, xperm_job).  These cases
+# activations are scaled by a power of two taken from the row's largest exponent and split into three e5m2 pieces
+# (bd_umma.cu, row-scale pass + xperm_job; host-side model in tests/test_d8_split_model.py).  These cases
 # leave the randn scale every other test uses: the result must stay inside the SAME tolerance whatever the magnitude of
 # the row, like the reference, which accumulates the unrounded activation (binary_gemm_kernel.py:260-278).
-SCALES = [1e-12, 1e-6, 1e-4, 1e-3, 1.0, 1e3, 6e4, 1e9]
+SCALES = [1e-30, 1e-12, 1e-6, 1e-4, 1e-3, 1.0, 1e3, 6e4, 1e9, 1e30]
 
 
 def _tenant_problem(T, m, K, N, seed):
@@ -869,9 +870,9 @@ def test_wide_dynamic_range_rows(kernel):
     assert torch.isfinite(got).all()
 
 
-def test_non_finite_and_out_of_range_activations_are_not_clipped():
-    # inf / NaN / |x| >= 2^60 in one tenant's row: that tenant's outputs are non-finite (never a silently saturated
-    # number), the other tenants are unaffected
+def test_non_finite_and_huge_activations_are_not_clipped():
+    # inf / NaN in one tenant's row: that tenant's outputs are non-finite (never a silently saturated number), the other
+    # tenants are unaffected; a huge but finite activation (2^70, far outside e5m2's own range) is just another row maximum
     T, m, K, N = 6, 1, 1024, 256
     _, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 13)
     x = x.bfloat16()
@@ -881,20 +882,29 @@ def test_non_finite_and_out_of_range_activations_are_not_clipped():
     mod = bd.DiffCompressModule(lin, masks, coeffs)
     mod.kernel = "umma"
     y_ref = mod(x).clone()
-    for t, bad in ((1, float("inf")), (3, float("nan")), (4, 2.0**70)):
+    for t, bad in ((1, float("inf")), (3, float("nan")), (4, float("-inf"))):
         xb = x.clone()
         xb[t, 0, 517] = bad
+        others = [i for i in range(T) if i != t]
         for y in (mod(xb), bd.binary_bmm(xb, masks, kernel="umma")):
             assert not torch.isfinite(y[t]).any(), f"tenant {t} with {bad}"
-            others = [i for i in range(T) if i != t]
             assert torch.isfinite(y[others]).all()
         assert torch.equal(mod(xb)[others], y_ref[others])
+    xb = x.clone()
+    xb[4, 0, 517] = 2.0**70
+    xb[2, 0, 3] = -(2.0**-90)
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact_d = torch.bmm(xb.double(), signs)
+    c = bd.binary_bmm(xb, masks, kernel="umma")
+    assert torch.isfinite(c.float()).all()
+    for t in range(T):
+        assert_close_to_exact(c[t], exact_d[t].cpu().numpy(), f"tenant {t} with a 2^70 outlier in tenant 4")
 
 
-def test_bucket_set_changes_from_block_to_block():
-    # The 8-bit decode path rewrites only the exponent buckets that are live now or were live the last time the same
-    # A-buffer tile was written.  Here every 64-wide K block has its own magnitude (some blocks are all zero), so the live
-    # set changes with every unit and stale pieces of an earlier unit would show up as an error.
+def test_magnitude_changes_from_block_to_block():
+    # The 8-bit decode path scales a row by ONE power of two per CTA (taken from the largest exponent inside the CTA's K
+    # range) and different CTAs see different K ranges.  Here every 64-wide K block has its own magnitude (some blocks are
+    # all zero), so neighbouring CTAs pick different scales and the split of the small blocks runs far below the row maximum.
     T, m, K, N = 6, 1, 8192, 640
     gen, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 17)
     expo = torch.tensor([-12.0, -6.0, 0.0, 6.0, 11.0], device=DEV)[torch.randint(0, 5, (T, K // 64), generator=gen, device=DEV)]
