@@ -13,14 +13,45 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+// ---- optional concurrent MMA stream (the kernel's per-unit mix: 4 bf16 SS MMAs N=16 + 12 e4m3 x e5m2 TS MMAs N=8, K=32) ----
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDesc8LoLbo = (128u >> 4) << 16;
+constexpr uint32_t kDesc8Hi = (512u >> 4) | (1u << 14);
+__device__ __forceinline__ void mma_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts8(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}" ::"r"(d), "r"(a_tmem), "r"(b_lo | kDesc8LoLbo), "r"(kDesc8Hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // MODE 0: full loop; 1: no tcgen05.st (registers consumed by an empty asm); 2: stores only (no ALU: constant registers)
 template <int MODE>
-__global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpack_warps, int spinners, long long* out) {
+__global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpack_warps, int spinners, long long* out, int with_mma) {
+  __shared__ __align__(1024) uint8_t tiles[16384 + 4096];  // a W tile (SWIZZLE_128B) and B operand tiles; contents are irrelevant
+  __shared__ uint64_t bar_mma;
   __shared__ uint32_t words[12 * 128 * 2];
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int flag;
   for (int i = threadIdx.x; i < 12 * 128 * 2; i += blockDim.x) words[i] = in[i];
-  if (threadIdx.x == 0) flag = 0;
+  if (threadIdx.x == 0) {
+    flag = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_mma)), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (16384 + 4096) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
@@ -66,6 +97,52 @@ __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpa
     t1 = clock64();
     __syncwarp();
     if (threadIdx.x == 0) flag = 1;
+  } else if (with_mma && warp == 15) {
+    // MMA issuer: per unit 4 SS + 12 TS MMAs and a commit; at most 2 units in flight (waits on the commit of unit u-2)
+    const bool leader = elect_one();
+    const uint32_t w_lo = (smem_u32(tiles) & 0x3FFFFu) >> 4, x_lo = (smem_u32(tiles + 16384) & 0x3FFFFu) >> 4;
+    const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_d = (1u << 4) | (0u << 7) | (1u << 10) | ((8u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t phase = 0;
+    int v = 0, ucount = 0;
+    const long long m0 = clock64();
+    for (int u = 0; v == 0; ++u, ++ucount) {
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_ss(tmem_base + 400, w_lo + ks * 2, x_lo + ks * 2, idesc_b, 1u);
+          if ((ks & 1) == 0)
+            for (int t = 0; t < 6; ++t) mma_ts8(tmem_base + 416 + t * 8, tmem_base + (u & 1) * 192 + t * 16 + (ks >> 1) * 8, x_lo + 16 + t * 32 + (ks >> 1) * 16, idesc_d, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
+      }
+      __syncwarp();
+      while (!mbar_try_wait(&bar_mma, phase)) {}
+      phase ^= 1u;
+      asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
+    }
+    if (lane == 0 && blockIdx.x == 0) { out[13] = clock64() - m0; out[14] = ucount; }
+  } else if (with_mma >= 2 && warp < unpack_warps + spinners) {
+    // instruction-cache probe: the other warps run a dependent ALU chain at the same issue rate either from a 16-instruction
+    // loop (with_mma == 2) or from a 1024-instruction straight-line body = 16 KB of code (with_mma == 3)
+    uint32_t x = lane, v = 0;
+    if (with_mma == 2) {
+      do {
+#pragma unroll 1
+        for (int rep = 0; rep < 64; ++rep) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(i * 77u + 1u), "r"(0x9e3779b9u));
+        }
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
+      } while (v == 0);
+    } else {
+      do {
+#pragma unroll
+        for (int i = 0; i < 1024; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(i * 77u + 1u), "r"(0x9e3779b9u));
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
+      } while (v == 0);
+    }
+    if (x == 0x12345u) out[15] = x;
   } else if (warp < unpack_warps + spinners) {
     // waiting roles: poll a shared-memory word (ld.acquire) like wait_released() does
     int v;
@@ -79,18 +156,19 @@ __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpa
 }
 
 template <int MODE>
-void run(const char* name, const uint32_t* in, long long* out, int unpack_warps, int spinners) {
+void run(const char* name, const uint32_t* in, long long* out, int unpack_warps, int spinners, int with_mma = 0) {
   const int units = 400;
-  k<MODE><<<148, 512>>>(in, 10, unpack_warps, spinners, out);
-  k<MODE><<<148, 512>>>(in, units, unpack_warps, spinners, out);
+  k<MODE><<<148, 512>>>(in, 10, unpack_warps, spinners, out, with_mma);
+  k<MODE><<<148, 512>>>(in, units, unpack_warps, spinners, out, with_mma);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
   long long h[16];
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   double mx = 0;
   for (int w = 0; w < unpack_warps; ++w) mx = h[w] > mx ? h[w] : mx;
-  printf("%-28s unpack warps %2d, spinning warps %d: %7.1f cycles per unit per warp (12 stores of 1 KB) -> %6.1f cycles per SM-unit of 48 KB\n", name,
-         unpack_warps, spinners, mx / units, mx / units * 4.0 / unpack_warps);
+  if (with_mma == 1) printf("   MMA warp: %lld units of 4 SS + 12 TS MMAs + commit + wait in %lld cycles = %.1f cycles per unit\n", h[14], h[13], (double)h[13] / (double)h[14]);
+  printf("%-28s %s unpack warps %2d, spinning warps %d: %7.1f cycles per unit per warp (12 stores of 1 KB) -> %6.1f cycles per SM-unit of 48 KB\n", name,
+         with_mma == 1 ? "+ concurrent MMA stream," : with_mma == 2 ? "+ ALU chain, 16-instr loop," : with_mma == 3 ? "+ ALU chain, 16 KB body," : "", unpack_warps, spinners, mx / units, mx / units * 4.0 / unpack_warps);
 }
 
 int main() {
@@ -101,6 +179,12 @@ int main() {
     run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp);
     run<1>("LDS + ALU only", in, out, uw, sp);
     run<2>("LDS + tcgen05.st only", in, out, uw, sp);
+    run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 1);
+    run<2>("LDS + tcgen05.st only", in, out, uw, sp, 1);
+    if (sp) {
+      run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 2);
+      run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 3);
+    }
   }
   return 0;
 }
