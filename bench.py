@@ -545,6 +545,73 @@ def run_model_step(torch, bd, dev, steps: int, warmup: int, prompt_len: int = 64
     return out
 
 
+# BASELINE configs 2 and 4: (name, N_out, K_in) per decoder layer
+LLAMA7B_LINEARS = [("q_proj", 4096, 4096), ("k_proj", 4096, 4096), ("v_proj", 4096, 4096), ("o_proj", 4096, 4096),
+                   ("gate_proj", 11008, 4096), ("up_proj", 11008, 4096), ("down_proj", 4096, 11008)]
+LLAMA13B_LINEARS = [("q_proj", 5120, 5120), ("k_proj", 5120, 5120), ("v_proj", 5120, 5120), ("o_proj", 5120, 5120),
+                    ("gate_proj", 13824, 5120), ("up_proj", 13824, 5120), ("down_proj", 5120, 13824)]
+
+
+def run_other_config(torch, bd, dist, dev, rank, world, stream, barrier, name, linears, layers, tenants_total, steps, warmup, prefill_tokens):
+    """The hot path of another BASELINE config: all BinaryDiff linears of a random-init model of that shape, `tenants_total`
+    deltas split over the ranks (delta sharding, every rank keeps the whole W_base), one decode step = one new token per
+    tenant (CUDA graph, q/k/v and gate/up grouped) and, optionally, a prefill pass of `prefill_tokens` tokens per tenant."""
+    if tenants_total % world != 0:
+        return None
+    T = tenants_total // world
+    hid = linears[0][2]
+    inter = linears[-1][2]
+    gen = torch.Generator(device=dev).manual_seed(31 + rank)
+    mods = []
+    for _ in range(layers):
+        layer = {}
+        for nm, n, k in linears:
+            lin = torch.nn.Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16)
+            with torch.no_grad():
+                lin.weight.normal_(0.0, 0.02, generator=gen)
+            masks = torch.randint(-(2**31), 2**31 - 1, (T, k // 32, n), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            coeffs = (torch.rand(T, generator=gen, device=dev) * 0.002 + 0.001).to(torch.bfloat16)
+            layer[nm] = bd.DiffCompressModule(lin, masks, coeffs)
+        _group(bd, layer)
+        mods.append(layer)
+    x_h = torch.randn(T, 1, hid, generator=gen, device=dev).bfloat16()
+    x_m = torch.randn(T, 1, inter, generator=gen, device=dev).bfloat16()
+    torch.cuda.synchronize(dev)
+    bytes_step = sum(2 * n * k + T * n * k // 8 + 2 * T * (k + n) for _, n, k in linears) * layers
+    out = {"model": name, "layers": layers, "tenants_total": tenants_total, "tenants_per_gpu": T, "n_gpus": world}
+    with torch.cuda.stream(stream):
+        mistral_step(mods, x_h, x_h, x_m)
+        torch.cuda.synchronize(dev)
+        ms, _ = graph_time_ms(torch, lambda: mistral_step(mods, x_h, x_h, x_m), stream, dev, steps, warmup, barrier)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t[0].item()
+        out["decode"] = {"ms_per_step": ms, "tokens_s": tenants_total / (ms * 1e-3), "bytes_per_gpu_per_step": bytes_step,
+                         "hbm_frac_per_gpu": bytes_step / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
+        if prefill_tokens:
+            xp_h = torch.randn(T, prefill_tokens, hid, generator=gen, device=dev).bfloat16()
+            xp_m = torch.randn(T, prefill_tokens, inter, generator=gen, device=dev).bfloat16()
+            mistral_step(mods[:1], xp_h, xp_h, xp_m)  # warm-up on one layer
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            mistral_step(mods, xp_h, xp_h, xp_m)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = t[0].item()
+            flops = sum(4 * tenants_total * prefill_tokens * n * k for _, n, k in linears) * layers
+            out["prefill"] = {"tokens_per_tenant": prefill_tokens, "ms": pms, "tflops_all_gpus": flops / (pms * 1e-3) / 1e12,
+                              "tokens_s": tenants_total * prefill_tokens / (pms * 1e-3),
+                              "frac_of_bf16_peak_per_gpu": flops / world / (pms * 1e-3) / 1e12 / measured_peaks()[1]}
+    del mods
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_tenant_strong(torch, bd, dist, dev, rank, world, mods, stream, steps, warmup, barrier, grouped, gen):
     """Strong scaling of tenant sharding: a FIXED set of 8 tenants split over the ranks (8 / world each), every rank still
     streaming its whole W_base replica -- the sub-linear curve SURVEY.md 8e predicts (per-GPU bytes 2NK + (T/G) NK/8)."""
@@ -742,6 +809,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         torch.cuda.empty_cache()
         tp = run_tp(torch, bd, dist, dev, rank, world, stream, max(args.steps, 10), args.warmup, barrier, args.tp_layers)
         torch.cuda.empty_cache()
+    other_configs = None
+    if not args.no_extras:
+        other_configs = []
+        # config 2: Llama-2-7B + one delta on one GPU (replicated per rank at N > 1); config 4: Llama-2-13B + 4 deltas,
+        # prefill 4096 + decode, delta-sharded over 1 / 2 / 4 GPUs
+        if world == 1:
+            other_configs.append(run_other_config(torch, bd, dist, dev, rank, world, stream, barrier, "Llama-2-7B + 1 delta (config 2)",
+                                                  LLAMA7B_LINEARS, 32, 1, max(args.steps // 2, 5), args.warmup, 2048))
+        if world in (1, 2, 4):
+            other_configs.append(run_other_config(torch, bd, dist, dev, rank, world, stream, barrier, "Llama-2-13B + 4 deltas (config 4)",
+                                                  LLAMA13B_LINEARS, 40, 4, max(args.steps // 2, 5), args.warmup, 4096))
+        other_configs = [c for c in other_configs if c is not None]
     # ---- the reference's own GPU path (Triton) under the same harness: single-GPU runs only (it is not a scaling leg) ----
     if rank == 0 and world == 1 and not args.no_triton_ref:
         triton_ref = run_triton_reference(torch, mods, (x_h, x_a, x_m), y_static, stream, dev, max(args.steps // 5, 3))
@@ -805,6 +884,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             line["tenant_leaves"] = leaves
         if strong is not None:
             line["tenant_strong_scaling"] = strong
+        if other_configs:
+            line["other_configs"] = other_configs
         if tp is not None:
             line["tp"] = tp
         if model_step is not None:

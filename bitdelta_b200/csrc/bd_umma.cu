@@ -206,7 +206,7 @@ struct UmmaArgs {
 // compiles them to the constant 0 and has no trace instantiation, no mutable globals and no bd_debug_* entry points.
 // bit 0 = stream the operands but skip unpack / MMA / epilogue, bit 2 = producer waits for the TMEM rendezvous,
 // bit 3 = unpack warps split tenants (not units), bit 4 = unpack without tcgen05.st, bit 5 = no MMAs (commits only),
-// bit 6 = no activation permute / split.
+// bit 6 = no activation permute / split, bit 7 = no row-scale scan (rows assumed to peak in [1, 2)).
 #ifdef BD_BRINGUP
 __device__ __forceinline__ int dbg_flags(const UmmaArgs& a) { return a.dbg; }
 #else
@@ -414,6 +414,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // elements become NaN pieces (the row's outputs are NaN, like the reference's).
   // The unpack and permute warps scan the rows (from L2: T x <= K values per CTA) while the first stages are in flight.
   if constexpr (DELTA8) {
+    if (dbg_flags(a) & 128) {  // bring-up A/B: no scan, rows assumed to peak in [1, 2)
+      if (threadIdx.x < kD8MaxTenants) s_rowexp[threadIdx.x] = 127;
+      if (warp < kWarpSync) named_bar_sync(kBarRowScale, kWarpSync * 32);  // (orders the stores above)
+    } else
     if (warp < kWarpSync) {
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are produced by the previous kernel of the stream
       constexpr int kScanThreads = kWarpSync * 32;
@@ -428,13 +432,16 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         if (kb >= a.kblocks) kb -= a.kblocks;
         const int k = kb * kBlockK + (ci & 7) * 8;
         if (k < a.K) {  // K % 8 == 0: a chunk is inside the row or outside it
+          // all tenants' loads first (independent L2 requests in flight), then the comparisons
+          // (unconditional: rows past the last tenant re-read the last tenant's chunk, an L2 hit, instead of predicating
+          // the loads -- predicated loads ended up serialised through one destination register)
+          uint4 v[10];
+#pragma unroll
+          for (int t = 0; t < 10; ++t) v[t] = __ldcg(reinterpret_cast<const uint4*>(xg + (size_t)min(t, a.T - 1) * a.K + k));
 #pragma unroll
           for (int t = 0; t < 10; ++t) {
-            if (t < a.T) {
-              const uint4 v = __ldcg(reinterpret_cast<const uint4*>(xg + (size_t)t * a.K + k));
-              // exponent fields of the two bf16 halves of a word, compared as packed unsigned 16-bit values
-              mx[t] = __vmaxu2(__vmaxu2(mx[t], v.x & 0x7F807F80u), __vmaxu2(v.y & 0x7F807F80u, __vmaxu2(v.z & 0x7F807F80u, v.w & 0x7F807F80u)));
-            }
+            // exponent fields of the two bf16 halves of a word, compared as packed unsigned 16-bit values
+            mx[t] = __vmaxu2(__vmaxu2(mx[t], v[t].x & 0x7F807F80u), __vmaxu2(v[t].y & 0x7F807F80u, __vmaxu2(v[t].z & 0x7F807F80u, v[t].w & 0x7F807F80u)));
           }
         }
       }
@@ -446,7 +453,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           if (lane == 0 && wmax != 0u) atomicMax(&s_rowexp[t], (int)wmax);
         }
       }
-      named_bar_sync(kBarRowScale, kScanThreads);
+      // Only the permute warps need the scales right away; the unpack warps read them in the epilogue (ordered behind this
+      // barrier through the MMA completion they wait for), so they arrive without waiting and go on to their first unit.
+      if (warp >= kWarpXperm0) named_bar_sync(kBarRowScale, kScanThreads);
+      else named_bar_arrive(kBarRowScale, kScanThreads);
     }
   }
   // scale applied to tenant t's activations before the split, as the exponent field of a float: 2^(kD8TopExp - (emax - 127)),
