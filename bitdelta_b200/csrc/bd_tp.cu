@@ -39,9 +39,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
   float4 v;
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -72,17 +69,21 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_kernel(const TpArgs a
     for (int r = 0; r < a.world; ++r)
       reinterpret_cast<float4*>(a.bufs[r] + par_off + (size_t)a.rank * a.slot_bytes)[i] = v;
   }
-  // 2. the last CTA to finish pushing publishes the epoch to every rank
+  // 2. the last CTA to finish pushing publishes the epoch to every rank.  Every CTA fences its pushes at system scope
+  //    BEFORE it counts itself in, so when the last one arrives all of this rank's data is already performed at the peers:
+  //    the flags can then go out as plain stores, one per thread, in parallel (a release store per peer from one thread
+  //    serialised eight NVLink round trips: 26 us per exchange at 8 ranks).
+  __shared__ unsigned s_last;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(hdr + 1, 1u);
-    if (t == gridDim.x - 1) {
-      hdr[1] = 0u;
-      __threadfence_system();
-      for (int r = 0; r < a.world; ++r) st_release_sys(reinterpret_cast<unsigned*>(a.bufs[r] + 128) + a.rank, e);
-    }
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) hdr[1] = 0u;
   }
+  __syncthreads();
+  if (s_last && threadIdx.x < a.world)
+    *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(a.bufs[threadIdx.x] + 128) + a.rank) = e;
   // 3. wait until every rank has published this epoch (flags in the LOCAL buffer; bounded spin -> trap, never a hang)
   if (threadIdx.x < a.world) {
     const unsigned* f = reinterpret_cast<const unsigned*>(mine + 128) + threadIdx.x;

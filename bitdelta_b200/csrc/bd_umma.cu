@@ -421,9 +421,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     if (warp < kWarpSync) {
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are produced by the previous kernel of the stream
       constexpr int kScanThreads = kWarpSync * 32;
+      constexpr bool kIsBf16 = std::is_same<T16, __nv_bfloat16>::value;
+      constexpr uint32_t kExpMask = kIsBf16 ? 0x7F807F80u : 0x7C007C00u;  // exponent fields of a packed pair
+      constexpr int kExpShift = kIsBf16 ? 7 : 10;
+      constexpr int kExpRebias = kIsBf16 ? 0 : 127 - 15;                  // s_rowexp holds fp32-biased exponents
       const int nkb = min(u_end - u_begin, a.kblocks);    // K blocks kb0, kb0 + 1, ... (mod kblocks) of this CTA's run
       const int chunks = nkb * (kBlockK / 8);             // 16-byte chunks (8 values) per row
-      const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x);
+      const T16* xg = reinterpret_cast<const T16*>(a.x);
       uint32_t mx[10];
 #pragma unroll
       for (int t = 0; t < 10; ++t) mx[t] = 0u;
@@ -441,16 +445,18 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll
           for (int t = 0; t < 10; ++t) {
             // exponent fields of the two bf16 halves of a word, compared as packed unsigned 16-bit values
-            mx[t] = __vmaxu2(__vmaxu2(mx[t], v[t].x & 0x7F807F80u), __vmaxu2(v[t].y & 0x7F807F80u, __vmaxu2(v[t].z & 0x7F807F80u, v[t].w & 0x7F807F80u)));
+            mx[t] = __vmaxu2(__vmaxu2(mx[t], v[t].x & kExpMask), __vmaxu2(v[t].y & kExpMask, __vmaxu2(v[t].z & kExpMask, v[t].w & kExpMask)));
           }
         }
       }
 #pragma unroll
       for (int t = 0; t < 10; ++t) {
         if (t < a.T) {
-          const uint32_t e = max(mx[t] & 0xFFFFu, mx[t] >> 16) >> 7;
+          const uint32_t e = max(mx[t] & 0xFFFFu, mx[t] >> 16) >> kExpShift;
           const uint32_t wmax = __reduce_max_sync(0xffffffffu, e);
-          if (lane == 0 && wmax != 0u) atomicMax(&s_rowexp[t], (int)wmax);
+          // (an fp16 subnormal row maximum, field 0, is below 2^-14: field 1's exponent is a valid upper bound; a bf16
+          // subnormal, field 0, takes the clamped largest scale, which cannot overflow it)
+          if (lane == 0) atomicMax(&s_rowexp[t], (int)(kIsBf16 ? wmax : max(wmax, 1u)) + kExpRebias);
         }
       }
       // Only the permute warps need the scales right away; the unpack warps read them in the epilogue (ordered behind this
@@ -466,6 +472,8 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   // K-permuted copy of the activation rows for A buffer `b` (see the header comment): job = (row r, 16-byte output
   // chunk c of the 64-K block); out chunk c of a 32-group = x[4c..4c+3] interleaved with x[4c+16..4c+19]; source and
   // destination tiles use the 128-byte swizzle (chunk index XOR row % 8).
+  // pieces per activation on the 8-bit path: 3 + 3 + 2 significant bits cover bf16's 8, 3 + 3 + 3 + 2 cover fp16's 11
+  constexpr int kD8Pieces = std::is_same<T16, __nv_bfloat16>::value ? 3 : 4;
   auto xperm_job = [&](const uint8_t* xsrc, uint8_t* xp, int job, uint32_t scale_field) {
     if constexpr (DELTA8) {
       // 8-bit delta path (one row per tenant).  job = (row r, 32-group g, c): one 32-bit output word per B-operand row,
@@ -485,16 +493,21 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // element 32g + c + 8q lives in 16-byte chunk 4g + q (swizzled by the row)
         const uint32_t bits = *reinterpret_cast<const unsigned short*>(src + (((4 * g + q) ^ (r & 7)) << 4));
-        bad |= ((bits & 0x7F80u) == 0x7F80u ? 0xFFu : 0u) << (8 * q);  // inf / NaN
-        f[q] = __uint_as_float(bits << 16) * scale;
+        if constexpr (std::is_same<T16, __nv_bfloat16>::value) {
+          bad |= ((bits & 0x7F80u) == 0x7F80u ? 0xFFu : 0u) << (8 * q);  // inf / NaN
+          f[q] = __uint_as_float(bits << 16) * scale;
+        } else {
+          bad |= ((bits & 0x7C00u) == 0x7C00u ? 0xFFu : 0u) << (8 * q);
+          f[q] = __half2float(__ushort_as_half((unsigned short)bits)) * scale;
+        }
       }
-      uint32_t pw[3];
+      uint32_t pw[kD8Pieces];
 #pragma unroll
-      for (int piece = 0; piece < 3; ++piece) {
+      for (int piece = 0; piece < kD8Pieces; ++piece) {
         const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[0], f[1]), __NV_SATFINITE, __NV_E5M2);
         const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[2], f[3]), __NV_SATFINITE, __NV_E5M2);
         pw[piece] = lo | (hi << 16);
-        if (piece < 2) {  // residuals: e5m2 is the top byte of fp16
+        if (piece < kD8Pieces - 1) {  // residuals: e5m2 is the top byte of fp16
           const uint32_t h01 = __byte_perm(lo, 0, 0x1404), h23 = __byte_perm(hi, 0, 0x1404);
           const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
           const float2 b23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
@@ -505,7 +518,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       // tenant tile: [8 rows x 64 B] as four 8-row x 16-byte core matrices; word c of the group sits at byte 32g + 4c
       uint8_t* tile = xp + r * 512 + (2 * g + (c >> 2)) * 128 + (c & 3) * 4;
 #pragma unroll
-      for (int piece = 0; piece < 3; ++piece) *reinterpret_cast<uint32_t*>(tile + piece * 16) = pw[piece];
+      for (int piece = 0; piece < kD8Pieces; ++piece) *reinterpret_cast<uint32_t*>(tile + piece * 16) = pw[piece];
       return;
     }
     const int r = job >> 3, c = job & 7;
@@ -864,7 +877,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
             tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 8, d0);
             if (HAS_BASE) bv = tmem_ld1(tmem_base + lane_addr + col_dbase + t);
             tc_wait_ld();
-            const float dsum = (d0[0] + d0[1] + d0[2]) * __uint_as_float((254u - d8_scale_field(t)) << 23);  // undo the row scale
+            const float dsum = (d0[0] + d0[1] + d0[2] + (kD8Pieces > 3 ? d0[3] : 0.f)) * __uint_as_float((254u - d8_scale_field(t)) << 23);  // undo the row scale
             const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
             if (full_k) {
               if (n < seg_n) store_y(y, (int64_t)t * seg_n + n, v, a.fp32_out);
@@ -1071,7 +1084,7 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
 // Picks the 8-bit delta path (e4m3 signs x e5m2 activation pieces: half the TMEM traffic, half the unpack work, half the
 // MMAs) whenever it applies -- bf16 activations, one row per tenant (decode) -- else the 16-bit path.
 UmmaPlan choose_plan(int dtype, int64_t T, int64_t m, int64_t K, int64_t N, bool has_base) {
-  if (dtype == BD_BF16 && m == 1 && !(g_dbg_flags & 2)) {
+  if ((dtype == BD_BF16 || dtype == BD_FP16) && m == 1 && !(g_dbg_flags & 2)) {
     UmmaPlan p8 = plan_umma(T, m, K, N, has_base, true);
     if (p8.ok) return p8;
   }
@@ -1263,6 +1276,9 @@ static int launch_one(const FwdProblem& p) {
     return has_base ? launch_typed<__nv_bfloat16, true, false, false, false>(p, plan, maps, a, grid)
                     : launch_typed<__nv_bfloat16, false, false, false, false>(p, plan, maps, a, grid);
   }
+  if (plan.d8)
+    return has_base ? launch_typed<__half, true, true, false, false>(p, plan, maps, a, grid)
+                    : launch_typed<__half, false, true, false, false>(p, plan, maps, a, grid);
   if (plan.natk)
     return has_base ? launch_typed<__half, true, false, true, false>(p, plan, maps, a, grid)
                     : launch_typed<__half, false, false, true, false>(p, plan, maps, a, grid);

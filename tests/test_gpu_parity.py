@@ -842,6 +842,36 @@ def test_activation_scale_does_not_change_the_error(kernel, m, scale):
         assert_close_to_exact(y, exact.cpu().numpy(), f"DiffCompressModule scale {scale:g}")
 
 
+@pytest.mark.parametrize("scale", [1e-7, 1e-6, 1e-4, 1e-2, 1.0, 1e2, 1e4])
+def test_activation_scale_fp16_decode(scale):
+    # fp16 activations (the dtype the reference's demo runs in, demo_backend.py:24) take the same 8-bit decode path with four
+    # pieces per element; the scales reach from fp16's subnormals to just below its overflow
+    T, m, K, N = 6, 1, 4096, 1024
+    gen, w, masks, coeffs, x = _tenant_problem(T, m, K, N, 41)
+    w, coeffs = w.half(), coeffs.half()
+    x = (x * scale).clamp(-60000.0, 60000.0).half()
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact_d = torch.bmm(x.double(), signs)
+    c = bd.binary_bmm(x, masks, kernel="umma")
+    assert torch.isfinite(c.float()).all() or scale >= 1e4  # sums of 4096 values near the top of fp16 may overflow the OUTPUT
+    if scale < 1e4:
+        assert_close_to_exact(c, exact_d.cpu().numpy(), f"binary_bmm fp16 scale {scale:g}")
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.float16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    for cf in (coeffs, (coeffs.float() * 300).half()):
+        mod = bd.DiffCompressModule(lin, masks, cf)
+        mod.kernel = "umma"
+        y = mod(x)
+        exact = x.double() @ w.double().T + cf.double()[:, None, None] * exact_d
+        # (the OUTPUT must be representable: skip sums that overflow fp16 or sit in its subnormal range, where half an ulp
+        # of the result is already more than the relative tolerance)
+        if exact.abs().max() < 6e4 and exact.abs().mean() > 1e-3:
+            assert_close_to_exact(y, exact.cpu().numpy(), f"DiffCompressModule fp16 scale {scale:g}")
+        elif exact.abs().max() < 6e4:
+            assert (y.double() - exact).abs().max() <= 2.0**-24 * 0.51 + 1e-3 * exact.abs().max()
+
+
 @pytest.mark.parametrize("kernel", ["umma", "simt"])
 def test_wide_dynamic_range_rows(kernel):
     # every row mixes magnitudes from 1e-9 to 1e9 (exponents drawn uniformly) plus a few massive outlier channels

@@ -5,9 +5,9 @@ mkdir -p gpurun_out
 timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 tail -c 400 gpurun_out/bench_final.err
 timeout 400 python tools/kernel_bench.py auto > gpurun_out/kernel_bench.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fwd_umma -c 256 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:fwd_umma -c 4 --csv --page raw --log-file gpurun_out/traffic_raw.csv python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-gemm > gpurun_out/ncu_traffic.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fwd_umma -s 2 -c 1 -o gpurun_out/gate_up_full -f python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-gemm > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fwd_umma -c 256 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm --no-extras --no-triton-ref --no-model-step > gpurun_out/ncu_launches.log 2>&1
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:fwd_umma -c 4 --csv --page raw --log-file gpurun_out/traffic_raw.csv python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-gemm --no-extras --no-triton-ref --no-model-step > gpurun_out/ncu_traffic.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fwd_umma -s 2 -c 1 -o gpurun_out/gate_up_full -f python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-gemm --no-extras --no-triton-ref --no-model-step > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -12
 python - <<'PY'
 import json
