@@ -206,7 +206,9 @@ struct UmmaArgs {
 // compiles them to the constant 0 and has no trace instantiation, no mutable globals and no bd_debug_* entry points.
 // bit 0 = stream the operands but skip unpack / MMA / epilogue, bit 2 = producer waits for the TMEM rendezvous,
 // bit 3 = unpack warps split tenants (not units), bit 4 = unpack without tcgen05.st, bit 5 = no MMAs (commits only),
-// bit 6 = no activation permute / split, bit 7 = no row-scale scan (rows assumed to peak in [1, 2)).
+// bit 6 = no activation permute / split, bit 7 = no row-scale scan (rows assumed to peak in [1, 2)),
+// bit 8 = half the sign work (only the first 32-K group of every unit is unpacked, stored and multiplied: wrong results, the
+// cost profile of a 4-bit sign operand).
 #ifdef BD_BRINGUP
 __device__ __forceinline__ int dbg_flags(const UmmaArgs& a) { return a.dbg; }
 #else
@@ -622,7 +624,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
           if (HAS_BASE) mma_ss_lo(d_base, w_lo + ks * 2, x_lo + ks * 2, idesc_base, acc);
           if constexpr (DELTA8) {
-            if ((ks & 1) == 0) {  // K = 32 per 8-bit MMA: two per tenant per unit
+            if ((ks & 1) == 0 && !((dbg_flags(a) & 256) && ks != 0)) {  // K = 32 per 8-bit MMA: two per tenant per unit
               const int k8 = ks >> 1;
               const uint32_t acc8 = (seg_first && k8 == 0) ? 0u : 1u;
               uint32_t d = d_delta, at = a_tmem0 + k8 * 8, bl = xp_lo + k8 * (256u >> 4);
@@ -738,6 +740,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
 #pragma unroll
           for (int jj = 0; jj < kBlockK / 32; ++jj) {
             const uint32_t w = wv[q][jj];
+            if (DELTA8 && (dbg_flags(a) & 256) && jj != 0) continue;  // bring-up: half the sign work (what a 4-bit operand would leave)
             if constexpr (DELTA8) {
               uint32_t r[8];
 #pragma unroll

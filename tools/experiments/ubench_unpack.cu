@@ -105,8 +105,11 @@ __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpa
     const uint32_t idesc_d = (1u << 4) | (0u << 7) | (1u << 10) | ((8u >> 3) << 17) | ((128u >> 4) << 24);
     uint32_t phase = 0;
     int v = 0, ucount = 0;
+    long long t_issue = 0, t_commit = 0, t_wait = 0;
     const long long m0 = clock64();
     for (int u = 0; v == 0; ++u, ++ucount) {
+      const long long ta = clock64();
+      long long tb = ta, tc = ta;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -114,14 +117,17 @@ __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpa
           if ((ks & 1) == 0)
             for (int t = 0; t < 6; ++t) mma_ts8(tmem_base + 416 + t * 8, tmem_base + (u & 1) * 192 + t * 16 + (ks >> 1) * 8, x_lo + 16 + t * 32 + (ks >> 1) * 16, idesc_d, 1u);
         }
+        tb = clock64();
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
+        tc = clock64();
       }
       __syncwarp();
       while (!mbar_try_wait(&bar_mma, phase)) {}
       phase ^= 1u;
+      if (leader) { t_issue += tb - ta; t_commit += tc - tb; t_wait += clock64() - tc; }
       asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
     }
-    if (lane == 0 && blockIdx.x == 0) { out[13] = clock64() - m0; out[14] = ucount; }
+    if (leader && blockIdx.x == 0) { out[13] = clock64() - m0; out[14] = ucount; out[10] = t_issue; out[11] = t_commit; out[12] = t_wait; }
   } else if (with_mma >= 2 && warp < unpack_warps + spinners) {
     // instruction-cache probe: the other warps run a dependent ALU chain at the same issue rate either from a 16-instruction
     // loop (with_mma == 2) or from a 1024-instruction straight-line body = 16 KB of code (with_mma == 3)
@@ -166,7 +172,7 @@ void run(const char* name, const uint32_t* in, long long* out, int unpack_warps,
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   double mx = 0;
   for (int w = 0; w < unpack_warps; ++w) mx = h[w] > mx ? h[w] : mx;
-  if (with_mma == 1) printf("   MMA warp: %lld units of 4 SS + 12 TS MMAs + commit + wait in %lld cycles = %.1f cycles per unit\n", h[14], h[13], (double)h[13] / (double)h[14]);
+  if (with_mma == 1) printf("   MMA warp: %lld units of 4 SS + 12 TS MMAs + commit + wait in %lld cycles = %.1f cycles per unit (issue of the 16 MMAs %.1f, commit %.1f, completion wait %.1f)\n", h[14], h[13], (double)h[13] / (double)h[14], (double)h[10] / h[14], (double)h[11] / h[14], (double)h[12] / h[14]);
   printf("%-28s %s unpack warps %2d, spinning warps %d: %7.1f cycles per unit per warp (12 stores of 1 KB) -> %6.1f cycles per SM-unit of 48 KB\n", name,
          with_mma == 1 ? "+ concurrent MMA stream," : with_mma == 2 ? "+ ALU chain, 16-instr loop," : with_mma == 3 ? "+ ALU chain, 16 KB body," : "", unpack_warps, spinners, mx / units, mx / units * 4.0 / unpack_warps);
 }
