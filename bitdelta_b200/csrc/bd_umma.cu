@@ -57,6 +57,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 24;
 // 8-bit delta path: every activation row is scaled by a power of two taken from the largest exponent of the row inside this
 // CTA's K range, so that its three e5m2 pieces sit in e5m2's exponent window (see the row-scale pass and xperm_job)
+constexpr bool kD8WideStore = false; // 8-bit path: tcgen05.st.x16 per tenant and unit (A/B against two .x8: see DESIGN.md 5b)
 constexpr int kD8MaxTenants = 16;   // rows of s_rowexp (the TMEM budget allows 10)
 constexpr int kBarRowScale = 12;    // named barrier of the row-scale pass (unpack + permute warps)
 constexpr int kD8TopExp = 14;       // the row maximum is scaled to [2^14, 2^15): the first piece stays below e5m2's 57344
@@ -737,6 +738,14 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         for (int q = 0; q < 3; ++q) {
           const int t = t0 + tstep * q;
           if (t >= a.T) break;
+          if (DELTA8 && kD8WideStore) {  // one 16-column store per tenant (both 32-K groups of the unit) instead of two 8-column stores
+            uint32_t r[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[c]) : "r"(wv[q][c >> 3] << (7 - (c & 7))), "r"(sign_mask), "r"(kOne));
+            tmem_st16(ta + t * 16, r);
+            continue;
+          }
 #pragma unroll
           for (int jj = 0; jj < kBlockK / 32; ++jj) {
             const uint32_t w = wv[q][jj];
