@@ -191,6 +191,10 @@ struct UmmaArgs {
   int unit_quantum;   // 1 = stream-K over single units; kblocks = whole (tile, row chunk) runs per CTA (no split-K fix-up)
   int m_chunks;       // row chunks of a.m rows each (prefill-size launches of one tenant); tile id = n_tile * m_chunks + chunk
   int m_total;        // rows of the tenant over all chunks
+  int tile_stride;    // 0: a CTA's tiles are consecutive; else (whole-tile launches of a multi-tenant prefill) CTA c works on
+                      // tiles c, c + stride, c + 2*stride, ...: all CTAs sweep the tile list together, one tenant at a time
+  int tpt;            // N tiles per tenant: tile column nt belongs to tenant nt / tpt (multi-tenant prefill: all tenants in one
+                      // launch, tenant outermost so that one tenant's activations stay in L2 while its tiles are swept)
   int stages;
   int n_abuf;         // TMEM A-operand buffers in use (2..kMaxABuf)
   int a_cols_tenant;  // TMEM columns of one tenant's sign tile per unit: 32 (16-bit signs) or 16 (e4m3 signs)
@@ -265,10 +269,19 @@ struct Ring {
 // Position in the unit space: K block kb of row chunk mc of N tile nt (tile id = nt * m_chunks + mc).
 struct UnitCursor {
   int nt, mc, kb;
-  __device__ __forceinline__ void next(int kblocks, int m_chunks) {
+  int tt;  // tenant of tile column nt (0 unless it is a multi-tenant prefill launch): tracked without a division per unit
+  __device__ __forceinline__ void next(int kblocks, int m_chunks, int tpt, int tile_stride) {
     if (++kb == kblocks) {
       kb = 0;
-      if (++mc == m_chunks) { mc = 0; ++nt; }
+      if (tile_stride) {  // strided whole-tile schedule: jump to tile id + stride (one division per tile)
+        const int tile = nt * m_chunks + mc + tile_stride;
+        nt = tile / m_chunks;
+        mc = tile - nt * m_chunks;
+        tt = nt / tpt;
+      } else if (++mc == m_chunks) {
+        mc = 0;
+        if (++nt - tt * tpt == tpt) ++tt;
+      }
     }
   }
 };
@@ -344,7 +357,9 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     a.trace[1024 + 4 * blockIdx.x + 2] = smid;
   }
   const int u_begin = cta_unit_begin(a, cta), u_end = cta_unit_begin(a, cta + 1);
-  const int tile0 = u_begin / a.kblocks, kb0 = u_begin - tile0 * a.kblocks;  // the only division by kblocks
+  // first tile: where the CTA's contiguous unit range starts -- or, with the strided whole-tile schedule, tile `cta`
+  const int tile0 = a.tile_stride ? cta : u_begin / a.kblocks;
+  const int kb0 = a.tile_stride ? 0 : u_begin - tile0 * a.kblocks;
   const int nt0 = tile0 / a.m_chunks, mc0 = tile0 - nt0 * a.m_chunks;       // n tile and row chunk of the first tile
   // The activation permutation is done by the dedicated warp alone when it is small (decode), otherwise shared with
   // the unpack warps.
@@ -543,7 +558,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // ===================================================== TMA producer
     if (lane == 0) {
       Ring st;
-      UnitCursor cur{nt0, mc0, kb0};
+      UnitCursor cur{nt0, mc0, kb0, nt0 / a.tpt};
       // Prologue under PDL: when the caller declares the weight and sign tiles static (BD_FLAG_STATIC_OPERANDS: long-lived
       // module buffers) those of the first `stages` units are requested right away; the activation tiles are produced by
       // the previous kernel of the stream, so those loads are issued only after griddepcontrol.wait.  Each stage's barrier
@@ -557,17 +572,17 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           uint8_t* sp = smem + (size_t)i * a.stage_bytes;
           mbar_arrive_expect_tx(&bar_full[i], a.tx_bytes);
           const int sg = (c2.nt >= a.seg_tile0[1]) + (c2.nt >= a.seg_tile0[2]);
-          const int lt = c2.nt - a.seg_tile0[sg];
+          const int lt = c2.nt - a.seg_tile0[sg] - c2.tt * a.tpt;
           if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[i], c2.kb * kBlockK, lt * kTileN, kEvictFirst);
-          tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[i], lt * kTileN, c2.kb * (kBlockK / 32), 0, kEvictFirst);
-          c2.next(a.kblocks, a.m_chunks);
+          tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[i], lt * kTileN, c2.kb * (kBlockK / 32), c2.tt, kEvictFirst);
+          c2.next(a.kblocks, a.m_chunks, a.tpt, a.tile_stride);
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int i = 0; i < npre; ++i) {
           trace_mark<TRACE>(a, i, 8);
-          tma_load_2d(smem + (size_t)i * a.stage_bytes + a.off_x, &tmap_x, &bar_full[i], cur.kb * kBlockK, cur.mc * a.m, kEvictLast);
+          tma_load_2d(smem + (size_t)i * a.stage_bytes + a.off_x, &tmap_x, &bar_full[i], cur.kb * kBlockK, cur.tt * a.m_total + cur.mc * a.m, kEvictLast);
           st.advance(a.stages);
-          cur.next(a.kblocks, a.m_chunks);
+          cur.next(a.kblocks, a.m_chunks, a.tpt, a.tile_stride);
         }
       }
 #pragma unroll 1
@@ -577,14 +592,14 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         uint8_t* sp = smem + (size_t)st.idx * a.stage_bytes;
         mbar_arrive_expect_tx(&bar_full[st.idx], a.tx_bytes);
         const int sg = (cur.nt >= a.seg_tile0[1]) + (cur.nt >= a.seg_tile0[2]);
-        const int lt = cur.nt - a.seg_tile0[sg];
+        const int lt = cur.nt - a.seg_tile0[sg] - cur.tt * a.tpt;
         // with row chunks the same W / sign tile is re-read for every chunk of the tile: keep it in L2 (evict-last)
         const uint64_t whint = a.m_chunks > 1 ? kEvictLast : kEvictFirst;
         if (HAS_BASE) tma_load_2d(sp, &maps.w[sg], &bar_full[st.idx], cur.kb * kBlockK, lt * kTileN, whint);
-        tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[st.idx], lt * kTileN, cur.kb * (kBlockK / 32), 0, whint);
-        tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], cur.kb * kBlockK, cur.mc * a.m, kEvictLast);
+        tma_load_3d(sp + a.off_masks, &maps.m[sg], &bar_full[st.idx], lt * kTileN, cur.kb * (kBlockK / 32), cur.tt, whint);
+        tma_load_2d(sp + a.off_x, &tmap_x, &bar_full[st.idx], cur.kb * kBlockK, cur.tt * a.m_total + cur.mc * a.m, kEvictLast);
         st.advance(a.stages);
-        cur.next(a.kblocks, a.m_chunks);
+        cur.next(a.kblocks, a.m_chunks, a.tpt, a.tile_stride);
       }
     }
   } else if (warp == kWarpMma) {
@@ -720,6 +735,16 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     asm volatile("" : "+r"(sign_mask));  // keep the mask in a register so mask + constant fit one LOP3
     Ring st, ab;
     int tile = tile0, nt = nt0, mc = mc0, kb = kb0, seg_kb0 = kb0;  // tile id = nt * m_chunks + mc
+    auto advance_tile = [&]() {
+      if (a.tile_stride) {
+        tile += a.tile_stride;
+        nt = tile / a.m_chunks;
+        mc = tile - nt * a.m_chunks;
+      } else {
+        ++tile;
+        if (++mc == a.m_chunks) { mc = 0; ++nt; }
+      }
+    };
     bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
     uint32_t dphase = 0;
     // Sign words of one unit -> +-1.0 operand registers -> TMEM A buffer `abi` (this warp's tenants, this thread's row).
@@ -852,7 +877,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       if ((dbg_flags(a) & 1) && seg_last) {
         mbar_wait(&bar_dfull, dphase);
         dphase ^= 1u;
-        if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
+        if (++kb == a.kblocks) { kb = 0; advance_tile(); }
         seg_kb0 = kb;
         seg_is_first = false;
         continue;
@@ -867,10 +892,11 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
         // which matrix of a grouped launch this tile belongs to
         const int sg = (nt >= a.seg_tile0[1]) + (nt >= a.seg_tile0[2]);
-        const int ltile = nt - a.seg_tile0[sg];
-        // row chunk of a prefill-size launch: rows [mc*m, mc*m + m_here) of the tenant
-        const int r_off = mc * a.m;
-        const int m_here = min(a.m, a.m_total - r_off);
+        // row chunk of a prefill-size launch: rows [mc*m, mc*m + m_here) of tenant tt (tt = 0 unless it is a multi-tenant prefill)
+        const int tt = nt / a.tpt;
+        const int ltile = nt - a.seg_tile0[sg] - tt * a.tpt;
+        const int r_off = tt * a.m_total + mc * a.m;
+        const int m_here = min(a.m, a.m_total - mc * a.m);
         const int64_t seg_n = a.n_seg[sg];
         T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
         const void* seg_coeff = a.coeff_seg[sg];
@@ -899,7 +925,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           }
         } else
         for (int t = 0; t < a.T; ++t) {
-          const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
+          const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t + tt) : 1.0f;
           for (int c8 = 0; c8 < a.mp / 8; ++c8) {
             if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
             if (c8 * 8 >= m_here) continue;
@@ -984,7 +1010,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         seg_is_first = false;
         if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 3] = clock64();
       }
-      if (++kb == a.kblocks) { kb = 0; ++tile; if (++mc == a.m_chunks) { mc = 0; ++nt; } }
+      if (++kb == a.kblocks) { kb = 0; advance_tile(); }
       if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
       if (tr) trace_mark<TRACE>(a, it, 13);
     }
@@ -1178,12 +1204,16 @@ size_t umma_workspace_bytes(int64_t rows, int64_t N) {
 static int launch_one(const FwdProblem& p) {
   int64_t T = p.T, m = p.m;
   // Prefill-size launches of ONE tenant are processed in row chunks of 128 inside the launch: tile = (N tile, row chunk)
+  // ... and so are multi-tenant launches with more than 16 rows per tenant (tile = (N tile, tenant, row chunk); inside the
+  // kernel it is a one-tenant problem per tile: the tile's tenant selects the sign words, the coefficient and the rows).
   const int64_t m_total = m;
+  const int64_t tenants_real = T;
   int64_t m_chunks = 1;
-  if (T == 1 && m > kMaxRows) {
+  if ((T == 1 && m > kMaxRows) || (T > 1 && m > 16)) {
     if (p.nseg > 1) return fail(BD_ERR_UNSUPPORTED, "grouped launch: more than %d rows", kMaxRows);
     m_chunks = (m + kMaxRows - 1) / kMaxRows;
-    m = kMaxRows;
+    if (m > kMaxRows) m = kMaxRows;
+    T = 1;
   }
   const bool has_base = p.w != nullptr;
   const int nseg = p.nseg < 1 ? 1 : p.nseg;
@@ -1228,7 +1258,8 @@ static int launch_one(const FwdProblem& p) {
   if (tiles > (int)(kWsCounterBytes / sizeof(unsigned))) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: too many N tiles");
   a.m_chunks = (int)m_chunks;
   a.m_total = (int)m_total;
-  const int64_t total_tiles = (int64_t)tiles * m_chunks;
+  a.tpt = tiles;  // tile columns [tt * tiles, (tt + 1) * tiles) belong to tenant tt
+  const int64_t total_tiles = (int64_t)tiles * m_chunks * (T == 1 ? tenants_real : 1);
   if (total_tiles * a.kblocks > 0x7fffffff) return fail(BD_ERR_UNSUPPORTED, "tcgen05 kernel: problem too large for one launch");
   a.n_tiles = (int)total_tiles;
   a.total_units = a.n_tiles * a.kblocks;
@@ -1237,6 +1268,9 @@ static int launch_one(const FwdProblem& p) {
   // stream-K over single units so that every SM streams the same number of bytes.
   const bool whole_tiles = total_tiles >= 4 * (int64_t)grid;
   a.unit_quantum = whole_tiles ? a.kblocks : 1;
+  // multi-tenant prefill: strided tiles, so that at any time all CTAs work on (about) the same tenant and its activations
+  // stay in L2 (with consecutive tiles per CTA every tenant's activations are live at once: 168 MB for 4 x 4096 x 5120)
+  a.tile_stride = (whole_tiles && T == 1 && tenants_real > 1) ? grid : 0;
   const int sched_units = whole_tiles ? a.n_tiles : a.total_units;
   a.units_per_cta = sched_units / grid;
   a.units_rem = sched_units % grid;
@@ -1264,13 +1298,13 @@ static int launch_one(const FwdProblem& p) {
       cuuint32_t box[2] = {kBlockK, kTileN};
       if ((rc = encode_map(&maps.w[sg], dt16, 2, ws[sg], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "w"))) return rc;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)Ns[sg], (cuuint64_t)(p.K / 32), (cuuint64_t)T};
+    cuuint64_t dims[3] = {(cuuint64_t)Ns[sg], (cuuint64_t)(p.K / 32), (cuuint64_t)tenants_real};
     cuuint64_t str[2] = {(cuuint64_t)Ns[sg] * 4, (cuuint64_t)strides[sg] * 4};
     cuuint32_t box[3] = {kTileN, kBlockK / 32, (cuuint32_t)T};
     if ((rc = encode_map(&maps.m[sg], CU_TENSOR_MAP_DATA_TYPE_INT32, 3, ms[sg], dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "masks"))) return rc;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)(T * m_total)}, str[1] = {(cuuint64_t)p.K * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)(tenants_real * m_total)}, str[1] = {(cuuint64_t)p.K * 2};
     cuuint32_t box[2] = {kBlockK, (cuuint32_t)plan.ntb};
     if ((rc = encode_map(&maps.x, dt16, 2, p.x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"))) return rc;
   }
@@ -1332,6 +1366,9 @@ int launch_fwd_umma(const FwdProblem& p0) {
     return rc;
   }
   if (choose_plan(p.dtype, p.T, p.m, p.K, p.N, has_base).ok) return launch_one(p);
+  // multi-tenant prefill: every tenant's row chunks in ONE launch
+  if (p.T > 1 && p.m > 16 && p.nseg <= 1 && p.T * p.m <= (1 << 20) && choose_plan(p.dtype, 1, p.m < kMaxRows ? p.m : kMaxRows, p.K, p.N, has_base).ok)
+    return launch_one(p);
   if (p.T > 1) {
     int g = p.m <= 16 ? tenants_per_launch(p.dtype, p.T, p.m, p.K, p.N, has_base) : 1;
     if (g < 1) g = 1;
