@@ -1019,6 +1019,28 @@ def test_multi_tenant_prefill_13b():
     assert_close_to_exact(y, _exact_forward(x, w, masks, coeffs).cpu().numpy(), "13B multi-tenant prefill")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,m,K,N", [(4, 600, 1024, 5120), (3, 130, 512, 8192), (2, 40, 2048, 384), (5, 129, 256, 128)])
+def test_multi_tenant_prefill_in_one_launch(T, m, K, N, dtype):
+    # more than 16 rows per tenant: all tenants' row chunks run in ONE launch (tile = (tenant, N tile, row chunk)); the first
+    # two shapes have enough tiles for the strided whole-tile schedule, the others take the stream-K path with split-K fix-up
+    gen = torch.Generator(device=DEV).manual_seed(T * 1000 + m)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.02).to(dtype)
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.3 + 0.05).to(dtype)  # large: a wrong tenant's signs or scale shows
+    x = torch.randn(T, m, K, generator=gen, device=DEV).to(dtype)
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=dtype)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    mod.kernel = "umma"
+    n0 = bd._lib.launch_count()
+    y = mod(x)
+    assert bd._lib.launch_count() - n0 == 1
+    assert_close_to_exact(y, _exact_forward(x, w, masks, coeffs).cpu().numpy(), f"T={T} m={m}")
+    assert torch.equal(y, mod(x))
+
+
 # ------------------------------------------------------------------------------------------------ launch flags
 @pytest.mark.parametrize("kernel", ["umma", "simt"])
 @pytest.mark.parametrize("T,m,K,N", [(8, 1, 1024, 8192), (2, 40, 512, 384), (1, 300, 1024, 512)])
