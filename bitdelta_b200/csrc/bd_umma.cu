@@ -212,6 +212,7 @@ struct UmmaArgs {
 // bit 0 = stream the operands but skip unpack / MMA / epilogue, bit 2 = producer waits for the TMEM rendezvous,
 // bit 3 = unpack warps split tenants (not units), bit 4 = unpack without tcgen05.st, bit 5 = no MMAs (commits only),
 // bit 6 = no activation permute / split, bit 7 = no row-scale scan (rows assumed to peak in [1, 2)),
+// bit 10 = sign stores without the conversion ALU work (wrong results; isolates the tcgen05.st path),
 // bit 8 = half the sign work (only the first 32-K group of every unit is unpacked, stored and multiplied: wrong results, the
 // cost profile of a 4-bit sign operand).
 #ifdef BD_BRINGUP
@@ -325,6 +326,33 @@ __device__ __forceinline__ void mma_ts8_lo(uint32_t d_tmem, uint32_t a_tmem, uin
       "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo | kDesc8LoLbo), "r"(kDesc8Hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with the LBO field already OR-ed into b_lo (per-tenant offsets are added to one pre-built low word: the address field
+// is 14 bits, offsets never carry into the LBO field at bit 16).
+__device__ __forceinline__ void mma_ts8_raw(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo_lbo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo_lbo), "r"(kDesc8Hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The 4 base + 2 * TT delta MMAs of one unit on the 8-bit path, for a COMPILE-TIME number of tenants: every operand is the
+// unit's base value plus a constant, so the one issuing thread -- the most loaded single role of the pipeline -- runs a
+// branch-free sequence (the generic loop over a run-time tenant count costs ~35 cycles per MMA, this one ~17).
+template <int TT, bool HAS_BASE>
+__device__ __forceinline__ void issue_unit_d8(uint32_t d_base, uint32_t d_delta, uint32_t w_lo, uint32_t x_lo, uint32_t a_tmem0,
+                                              uint32_t bl0, uint32_t idesc_base, uint32_t idesc_delta, uint32_t acc0) {
+#pragma unroll
+  for (int ks = 0; ks < kBlockK / 16; ++ks) {
+    if (HAS_BASE) mma_ss_lo(d_base, w_lo + ks * 2, x_lo + ks * 2, idesc_base, ks == 0 ? acc0 : 1u);
+    if ((ks & 1) == 0) {
+      const int k8 = ks >> 1;
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        mma_ts8_raw(d_delta + t * 8, a_tmem0 + k8 * 8 + t * 16, bl0 + k8 * (256u >> 4) + t * (512u >> 4), idesc_delta, k8 == 0 ? acc0 : 1u);
+    }
+  }
 }
 // kind::f8f6f4 instruction descriptor: A = e4m3 (0), B = e5m2 (1), fp32 accumulate, K-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc8(int n) {
@@ -635,6 +663,23 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         const uint32_t a_tmem0 = tmem_base + col_abuf0 + ab.idx * a_cols_per_buf;
         const uint32_t d_base = tmem_base + col_dbase, d_delta = tmem_base + col_ddelta;
         // k-step outermost: consecutive MMAs go to different accumulators (base, tenant 0, tenant 1, ...)
+        bool issued = false;
+        if constexpr (DELTA8) {
+          if (!(dbg_flags(a) & 256)) {
+            const uint32_t acc0 = seg_first ? 0u : 1u, bl0 = xp_lo | kDesc8LoLbo;
+            issued = true;
+            switch (a.T) {
+              case 1: issue_unit_d8<1, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              case 2: issue_unit_d8<2, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              case 3: issue_unit_d8<3, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              case 4: issue_unit_d8<4, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              case 6: issue_unit_d8<6, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              case 8: issue_unit_d8<8, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
+              default: issued = false; break;  // other tenant counts: the generic loop below
+            }
+          }
+        }
+        if (!issued)
 #pragma unroll
         for (int ks = 0; ks < kBlockK / 16; ++ks) {
           const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
@@ -783,6 +828,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
                 // r = (~sh & 0x80808080) | 0x38383838 : four e4m3 values, +1.0 = 0x38, -1.0 = 0xB8 (one LOP3, LUT 0xAE)
                 asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(r[c]) : "r"(sh), "r"(sign_mask), "r"(kOne));
               }
+              if (dbg_flags(a) & 1024) {  // bring-up: stores without the conversion (timing of the store path alone)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r[c] = w;
+              }
               if (dbg_flags(a) & 16) {
                 asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
               } else {
@@ -840,7 +889,10 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           named_bar_arrive(kBarAFull0 + ab_i.idx, afull_threads);  // this warp's rows of A buffer ab_i.idx are written
           if (tr) trace_mark<TRACE>(a, it, 11);
         }
-        for (int i = 0; i < g; ++i) { st.advance(a.stages); ab.advance(a.n_abuf); }
+        // (closed form, g <= 2 <= ring sizes: the generic per-step loop compiled into a long chain of branches that cost this
+        // warp ~10 % of its time; these warps only use the ring indices, not the phases)
+        st.idx += g; if (st.idx >= a.stages) st.idx -= a.stages;
+        ab.idx += g; if (ab.idx >= a.n_abuf) ab.idx -= a.n_abuf;
       } else {
       wait_released(&s_released, it + g - 1);
       tc_fence_after();

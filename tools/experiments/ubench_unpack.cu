@@ -40,14 +40,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 template <int MODE>
 __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpack_warps, int spinners, long long* out, int with_mma) {
   __shared__ __align__(1024) uint8_t tiles[16384 + 4096];  // a W tile (SWIZZLE_128B) and B operand tiles; contents are irrelevant
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_mma_arr[3];
+  uint64_t& bar_mma = bar_mma_arr[0];
   __shared__ uint32_t words[12 * 128 * 2];
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int flag;
   for (int i = threadIdx.x; i < 12 * 128 * 2; i += blockDim.x) words[i] = in[i];
   if (threadIdx.x == 0) {
     flag = 0;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_mma)), "r"(1u) : "memory");
+    for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_mma_arr[i])), "r"(1u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < (16384 + 4096) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x3c003c00u;
@@ -128,6 +129,13 @@ __global__ void __launch_bounds__(512) k(const uint32_t* in, int units, int unpa
       asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
     }
     if (leader && blockIdx.x == 0) { out[13] = clock64() - m0; out[14] = ucount; out[10] = t_issue; out[11] = t_commit; out[12] = t_wait; }
+  } else if (with_mma == 4 && warp < unpack_warps + spinners) {
+    // waiting roles that spin on an mbarrier (the kernel's sync warp and TMA producer): try_wait on a phase that never completes
+    int v = 0;
+    do {
+      for (int rep = 0; rep < 4; ++rep) (void)mbar_try_wait(&bar_mma + 1 + (warp & 1), 0);
+      asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&flag)) : "memory");
+    } while (v == 0);
   } else if (with_mma >= 2 && warp < unpack_warps + spinners) {
     // instruction-cache probe: the other warps run a dependent ALU chain at the same issue rate either from a 16-instruction
     // loop (with_mma == 2) or from a 1024-instruction straight-line body = 16 KB of code (with_mma == 3)
@@ -174,7 +182,7 @@ void run(const char* name, const uint32_t* in, long long* out, int unpack_warps,
   for (int w = 0; w < unpack_warps; ++w) mx = h[w] > mx ? h[w] : mx;
   if (with_mma == 1) printf("   MMA warp: %lld units of 4 SS + 12 TS MMAs + commit + wait in %lld cycles = %.1f cycles per unit (issue of the 16 MMAs %.1f, commit %.1f, completion wait %.1f)\n", h[14], h[13], (double)h[13] / (double)h[14], (double)h[10] / h[14], (double)h[11] / h[14], (double)h[12] / h[14]);
   printf("%-28s %s unpack warps %2d, spinning warps %d: %7.1f cycles per unit per warp (12 stores of 1 KB) -> %6.1f cycles per SM-unit of 48 KB\n", name,
-         with_mma == 1 ? "+ concurrent MMA stream," : with_mma == 2 ? "+ ALU chain, 16-instr loop," : with_mma == 3 ? "+ ALU chain, 16 KB body," : "", unpack_warps, spinners, mx / units, mx / units * 4.0 / unpack_warps);
+         with_mma == 1 ? "+ concurrent MMA stream," : with_mma == 2 ? "+ ALU chain, 16-instr loop," : with_mma == 3 ? "+ ALU chain, 16 KB body," : with_mma == 4 ? "+ mbarrier try_wait spinners," : "", unpack_warps, spinners, mx / units, mx / units * 4.0 / unpack_warps);
 }
 
 int main() {
@@ -190,6 +198,8 @@ int main() {
     if (sp) {
       run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 2);
       run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 3);
+      run<0>("LDS + ALU + tcgen05.st", in, out, uw, sp, 4);
+      run<2>("LDS + tcgen05.st only", in, out, uw, sp, 4);
     }
   }
   return 0;

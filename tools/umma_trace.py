@@ -16,6 +16,7 @@ coeff = torch.full((T,), 0.002, device=dev)
 x = torch.randn(T, m, K, generator=g, device=dev).bfloat16()
 for _ in range(3):
     _fused_forward(x, w, ms, coeff, T, "umma", static_operands=True)
+_lib.lib.bd_debug_set_flags(int(os.environ.get("BD_DBG_FLAGS", "0")), 0)  # A/B knobs of the bring-up library (see bd_umma.cu)
 buf = torch.zeros(64 * 16 + 4 * 160, dtype=torch.int64, device=dev)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 _lib.lib.bd_debug_set_trace(buf.data_ptr())
@@ -38,6 +39,12 @@ t0 = t[0, 8].item()
 k = t[63]
 print(f"kernel (CTA 0): entry->setup {k[1]-k[0]} cyc, setup->first TMA {t0-k[1]}, first TMA->last unit done {k[2]-t0}, last epilogue {k[3]-k[2]}, ->teardown {k[4]-k[3]}; total {k[4]-k[0]} cyc = {(k[9]-k[8])/1e3:.2f} us (globaltimer)")
 names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived", "U:s12", "U:s13"]
+rows = [[t[it, s_].item() for s_ in range(14)] for it in range(8, 56) if t[it, 1].item() and t[it + 2, 0].item()]
+if rows:
+    import statistics as st_
+    own = [b[0] - a[0] for a, b in zip(rows, rows[1:])]
+    print(f"traced unpack warp, per own unit (median): wait+fence {st_.median(r[1]-r[0] for r in rows):.0f}, unpack {st_.median(r[3]-r[1] for r in rows):.0f}, "
+          f"wait::st+fence {st_.median(r[4]-r[3] for r in rows):.0f}, arrive {st_.median(r[11]-r[4] for r in rows):.0f}, bookkeeping {st_.median(r[13]-r[11] for r in rows):.0f}; own-unit period {st_.median(own):.0f}")
 print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
 print("unit " + " ".join(n.rjust(9) for n in names))
 for it in range(64):
