@@ -21,7 +21,7 @@ shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [
 out = []
 for (T, m, K, N) in shapes:
     bytes_alg = 2 * N * K + T * N * K // 8 + 2 * T * m * (K + N)
-    n_sets = max(2, int(600e6 // bytes_alg) + 1)
+    n_sets = int(os.environ.get("BD_NSETS", "0")) or max(2, int(600e6 // bytes_alg) + 1)  # BD_NSETS=1: operands stay in L2 (consumer-side floor)
     g = torch.Generator(device=dev).manual_seed(0)
     ws = [(torch.randn(N, K, generator=g, device=dev) * 0.02).bfloat16() for _ in range(n_sets)]
     ms = [torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=g, device=dev, dtype=torch.int64).to(torch.int32) for _ in range(n_sets)]
