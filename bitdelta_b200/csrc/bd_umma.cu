@@ -495,16 +495,19 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           }
         }
       }
+      // warp maxima, tenant t's into lane t, then ONE shared-memory atomic per warp (one lane per tenant)
+      uint32_t mine = 0u;
 #pragma unroll
       for (int t = 0; t < 10; ++t) {
         if (t < a.T) {
           const uint32_t e = max(mx[t] & 0xFFFFu, mx[t] >> 16) >> kExpShift;
           const uint32_t wmax = __reduce_max_sync(0xffffffffu, e);
-          // (an fp16 subnormal row maximum, field 0, is below 2^-14: field 1's exponent is a valid upper bound; a bf16
-          // subnormal, field 0, takes the clamped largest scale, which cannot overflow it)
-          if (lane == 0) atomicMax(&s_rowexp[t], (int)(kIsBf16 ? wmax : max(wmax, 1u)) + kExpRebias);
+          if (lane == t) mine = wmax;
         }
       }
+      // (an fp16 subnormal row maximum, field 0, is below 2^-14: field 1's exponent is a valid upper bound; a bf16
+      // subnormal, field 0, takes the clamped largest scale, which cannot overflow it)
+      if (lane < a.T) atomicMax(&s_rowexp[lane], (int)(kIsBf16 ? mine : max(mine, 1u)) + kExpRebias);
       // Only the permute warps need the scales right away; the unpack warps read them in the epilogue (ordered behind this
       // barrier through the MMA completion they wait for), so they arrive without waiting and go on to their first unit.
       if (warp >= kWarpXperm0) named_bar_sync(kBarRowScale, kScanThreads);
