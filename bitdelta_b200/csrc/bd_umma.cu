@@ -407,30 +407,39 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- one-time setup ----
-  if (warp == kWarpProducer && lane == 0) {
-    for (int sg = 0; sg < a.nseg; ++sg) {
-      if (HAS_BASE) prefetch_tmap(&maps.w[sg]);
-      prefetch_tmap(&maps.m[sg]);
+  if (warp == kWarpProducer) {
+    // the producer warp's lanes initialise the mbarriers in parallel (one thread doing all ~21 of them cost ~0.3 us of every
+    // launch's prologue): lanes 0..7 the stage barriers, 8..15 the A-buffer barriers, 16 the accumulator barrier; lane 31
+    // prefetches the tensor maps
+    if (lane < kMaxStages) {
+      if (lane < a.stages) {
+        mbar_init(&bar_full[lane], 1);
+        // A stage is released by the MMA commit alone: the MMAs of a unit are issued only after every unpack warp and
+        // the permute warp have arrived on bar_afull, i.e. after they are done reading the stage.
+        mbar_init(&bar_empty[lane], 1);
+      }
+    } else if (lane < kMaxStages + kMaxABuf) {
+      if (lane - kMaxStages < a.n_abuf) mbar_init(&bar_aempty[lane - kMaxStages], 1);
+    } else if (lane == kMaxStages + kMaxABuf) {
+      mbar_init(&bar_dfull, 1);
+    } else if (lane == 31) {
+      for (int sg = 0; sg < a.nseg; ++sg) {
+        if (HAS_BASE) prefetch_tmap(&maps.w[sg]);
+        prefetch_tmap(&maps.m[sg]);
+      }
+      prefetch_tmap(&tmap_x);
     }
-    prefetch_tmap(&tmap_x);
-    for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&bar_full[s], 1);
-      // A stage is released by the MMA commit alone: the MMAs of a unit are issued only after every unpack warp and
-      // the permute warp have arrived on bar_afull, i.e. after they are done reading the stage.
-      mbar_init(&bar_empty[s], 1);
-    }
-    for (int b = 0; b < a.n_abuf; ++b) {
-      mbar_init(&bar_aempty[b], 1);
-    }
-    mbar_init(&bar_dfull, 1);
     fence_barrier_init();
+    __syncwarp();  // lane 0 (the TMA producer) uses barriers its sibling lanes initialised
   }
   if (threadIdx.x == 0) s_released = 0;
   if (DELTA8 && threadIdx.x < kD8MaxTenants) s_rowexp[threadIdx.x] = 0;
-  __syncthreads();  // mbarriers initialised
-  // The TMA producer needs nothing else: it starts requesting the first weight / sign stages right away, while the other
-  // warps allocate tensor memory and zero the permuted-activation tiles and rendezvous without it.
-  if (warp != kWarpProducer || (dbg_flags(a) & 4)) {
+  // ONE rendezvous for the whole prologue: the producer warp (which initialised the mbarriers above) only ARRIVES and starts
+  // requesting the first weight / sign stages right away; the other warps meanwhile allocate tensor memory and zero the
+  // permuted-activation tiles, then wait for each other and for the producer's arrival (= mbarriers initialised).
+  if (warp == kWarpProducer && !(dbg_flags(a) & 4)) {
+    named_bar_arrive(kBarTmemReady, kThreads);
+  } else {
     if (warp == kWarpMma) tmem_alloc(&tmem_base_slot, kTmemCols);
     // zero the permuted-activation tiles once: rows >= m of every tenant tile stay zero for the whole kernel
     const bool all = (dbg_flags(a) & 4) != 0;
@@ -440,7 +449,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       *reinterpret_cast<uint4*>(smem + a.off_xp + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
-    named_bar_sync(kBarTmemReady, (int)nparts);
+    named_bar_sync(kBarTmemReady, kThreads);
     tc_fence_after();
   }
   if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 1] = clock64();
