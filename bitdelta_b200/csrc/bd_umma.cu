@@ -371,7 +371,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_aempty[kMaxABuf], bar_dfull;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ unsigned s_is_last;
+  __shared__ unsigned s_is_last[2];
   __shared__ int s_released;  // number of units the sync warp has released to the unpack group (release/acquire)
   __shared__ int s_rowexp[kD8MaxTenants];  // 8-bit path: largest biased bf16 exponent of tenant t's row over this CTA's K range
 
@@ -803,6 +803,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       }
     };
     bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
+    int pend_tile0 = -1, pend_nt0 = 0, pend_mc0 = 0, pend_tile1 = -1, pend_nt1 = 0, pend_mc1 = 0;  // partial runs to publish
     uint32_t dphase = 0;
     // Sign words of one unit -> +-1.0 operand registers -> TMEM A buffer `abi` (this warp's tenants, this thread's row).
     auto unpack_unit = [&](const uint8_t* sp, int abi, int tfirst, int tstep) {
@@ -1020,56 +1021,16 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           }
         }
         tc_fence_before();
+        // every unpack warp has read its part of the accumulators: only now may any of them hand the MMA warp the first
+        // unit of the next run (with alternating units that hand-over involves only half of these warps)
+        asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
 
         if (!full_k) {
-          // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
-          const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
-          const int big = a.units_rem * (a.units_per_cta + 1);  // units owned by the CTAs that got one extra unit
-          const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
-          const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
-          __threadfence();
-          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-          if (ut == 0) {
-            const unsigned old = atomicAdd(&a.counters[tile], 1u);
-            s_is_last = (old == (unsigned)(c_last - c_first)) ? 1u : 0u;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-          if (s_is_last) {
-            __threadfence();
-            // Deterministic reduction with memory-level parallelism: work item = (output row r, 4 consecutive weight
-            // rows); the slots of all contributors are fetched with independent 16-byte L2 loads, 8 in flight per
-            // thread, and added in K order.  (A serial loop over ~18 contributors cost a 10 us tail per launch.)
-            const int items = (a.m_chunks > 1 ? m_here : a.rows) * (kTileN / 4);
-            for (int item = ut; item < items; item += kUnpackWarps * 32) {
-              const int r = item / (kTileN / 4), q4 = item - r * (kTileN / 4);
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int c0 = c_first; c0 <= c_last; c0 += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int c = c0 + j;
-                  v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (c <= c_last) {
-                    const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
-                    v[j] = __ldcg(reinterpret_cast<const float4*>(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN) + q4);
-                  }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-              }
-              const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
-              const int64_t o4 = (int64_t)(r_off + r) * seg_n + n4;
-              if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte (fp32: 16-byte) aligned for these 4 elements
-                if (a.fp32_out) {
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o4) = acc;
-                } else {
-                  const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
-                  *reinterpret_cast<uint2*>(y + o4) = *reinterpret_cast<const uint2*>(o);
-                }
-              }
-            }
-            if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
-          }
+          // split-K: this run's partial sums are in the CTA's slot; they are published (fence + arrival counter) after the
+          // CTA's last unit, together with the other partial run if there is one -- a CTA has at most two (the first and
+          // the last run of its unit range), and publishing the first one in mid-stream stalled the unpack warps for a
+          // fence, two barriers and an atomic round trip while the pipeline ran dry behind them.
+          if (slot == 0) { pend_tile0 = tile; pend_nt0 = nt; pend_mc0 = mc; } else { pend_tile1 = tile; pend_nt1 = nt; pend_mc1 = mc; }
         }
         seg_is_first = false;
         if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 3] = clock64();
@@ -1077,6 +1038,73 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       if (++kb == a.kblocks) { kb = 0; advance_tile(); }
       if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
       if (tr) trace_mark<TRACE>(a, it, 13);
+    }
+
+    // ---- split-K fix-up: publish the partial runs; the last CTA to arrive at a tile sums every contributor's slot in K order ----
+    if (pend_tile0 >= 0 || pend_tile1 >= 0) {
+      const int big = a.units_rem * (a.units_per_cta + 1);  // units owned by the CTAs that got one extra unit
+      auto owner = [&](int unit) { return unit < big ? unit / (a.units_per_cta + 1) : a.units_rem + (unit - big) / a.units_per_cta; };
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+      if (ut == 0 || ut == 32) {  // one thread per partial run: the two atomic round trips overlap
+        const int ptile = ut ? pend_tile1 : pend_tile0;
+        unsigned last = 0;
+        if (ptile >= 0) {
+          const int fu = ptile * a.kblocks;
+          last = atomicAdd(&a.counters[ptile], 1u) == (unsigned)(owner(fu + a.kblocks - 1) - owner(fu)) ? 1u : 0u;
+        }
+        s_is_last[ut ? 1 : 0] = last;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+      const unsigned last = s_is_last[0] | (s_is_last[1] << 1);
+      if (last) __threadfence();
+#pragma unroll 1
+      for (int p = 0; p < 2; ++p) {
+        if (!(last & (1u << p))) continue;
+        const int ptile = p ? pend_tile1 : pend_tile0, pnt = p ? pend_nt1 : pend_nt0, pmc = p ? pend_mc1 : pend_mc0;
+        const int first_unit = ptile * a.kblocks;
+        const int c_first = owner(first_unit), c_last = owner(first_unit + a.kblocks - 1);
+        const int sg = (pnt >= a.seg_tile0[1]) + (pnt >= a.seg_tile0[2]);
+        const int tt = pnt / a.tpt;
+        const int ltile = pnt - a.seg_tile0[sg] - tt * a.tpt;
+        const int r_off = tt * a.m_total + pmc * a.m;
+        const int m_here = min(a.m, a.m_total - pmc * a.m);
+        const int64_t seg_n = a.n_seg[sg];
+        T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
+        // Deterministic reduction with memory-level parallelism: work item = (output row r, 4 consecutive weight rows);
+        // the slots of all contributors are fetched with independent 16-byte L2 loads, 8 in flight per thread, and added
+        // in K order.  (A serial loop over ~18 contributors cost a 10 us tail per launch.)
+        const int items = (a.m_chunks > 1 ? m_here : a.rows) * (kTileN / 4);
+        for (int item = ut; item < items; item += kUnpackWarps * 32) {
+          const int r = item / (kTileN / 4), q4 = item - r * (kTileN / 4);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c0 = c_first; c0 <= c_last; c0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + j;
+              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c <= c_last) {
+                const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
+                v[j] = __ldcg(reinterpret_cast<const float4*>(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN) + q4);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+          }
+          const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
+          const int64_t o4 = (int64_t)(r_off + r) * seg_n + n4;
+          if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte (fp32: 16-byte) aligned for these 4 elements
+            if (a.fp32_out) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o4) = acc;
+            } else {
+              const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
+              *reinterpret_cast<uint2*>(y + o4) = *reinterpret_cast<const uint2*>(o);
+            }
+          }
+        }
+        if (ut == 0) a.counters[ptile] = 0u;  // leave the workspace clean for the next launch
+      }
     }
   }
 
