@@ -37,13 +37,14 @@ def _stale(out: str = OUT) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> str:
-    out_path = OUT_BRINGUP if bringup else OUT
+def build(force: bool = False, verbose: bool = False, bringup: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines` / `out`: compile-time A/B variants of the release library for tools/ab_variants.sh (never loaded by the package)."""
+    out_path = out or (OUT_BRINGUP if bringup else OUT)
     if not force and not _stale(out_path):
         return out_path
     nvcc = _nvcc()
-    objdir = os.path.join(PKG, "build", "bringup" if bringup else "release")
-    extra = ["-DBD_BRINGUP"] if bringup else []
+    objdir = os.path.join(PKG, "build", "variant_" + os.path.basename(out).replace(".so", "") if out else ("bringup" if bringup else "release"))
+    extra = (["-DBD_BRINGUP"] if bringup else []) + [f"-D{d}" for d in defines]
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -66,4 +67,6 @@ def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> 
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bringup="--bringup" in sys.argv))
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    _out = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv or bool(_out), verbose="-v" in sys.argv, bringup="--bringup" in sys.argv, defines=_defs, out=_out))

@@ -38,7 +38,7 @@ t = allt[:1024].view(64, 16)
 t0 = t[0, 8].item()
 k = t[63]
 print(f"kernel (CTA 0): entry->setup {k[1]-k[0]} cyc, setup->first TMA {t0-k[1]}, first TMA->last unit done {k[2]-t0}, last epilogue {k[3]-k[2]}, ->teardown {k[4]-k[3]}; total {k[4]-k[0]} cyc = {(k[9]-k[8])/1e3:.2f} us (globaltimer)")
-names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived", "U:s12", "U:s13"]
+names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived", "U:s12", "U:s13", "S:full", "S:aempty"]
 rows = [[t[it, s_].item() for s_ in range(14)] for it in range(8, 56) if t[it, 1].item() and t[it + 2, 0].item()]
 if rows:
     import statistics as st_
@@ -48,7 +48,7 @@ if rows:
 print(f"T={T} m={m} K={K} N={N}; cycles relative to the producer's first TMA issue")
 print("unit " + " ".join(n.rjust(9) for n in names))
 for it in range(64):
-    if not any(t[it, s].item() for s in range(14)):
+    if not any(t[it, s].item() for s in range(16)):
         break
-    row = [(t[it, s].item() - t0) if t[it, s].item() else -1 for s in range(14)]
+    row = [(t[it, s].item() - t0) if t[it, s].item() else -1 for s in range(16)]
     print(f"{it:4d} " + " ".join(str(v).rjust(9) for v in row))
