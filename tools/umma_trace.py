@@ -34,6 +34,11 @@ e0 = live[:, 0].min().item()
 ent = (live[:, 0] - e0).float() / 1e3
 ex = (live[:, 1] - e0).float() / 1e3
 print(f"grid: {live.shape[0]} CTAs; entry us min/median/max = {ent.min():.2f}/{ent.median():.2f}/{ent.max():.2f}; exit us min/median/max = {ex.min():.2f}/{ex.median():.2f}/{ex.max():.2f}; lifetime median {(ex-ent).median():.2f} max {(ex-ent).max():.2f}")
+if os.environ.get("BD_TRACE_CTAS"):  # per-CTA lifetimes: which CTAs end late, and on which SMs
+    lt_ = ((life[:, 1] - life[:, 0]).float() / 1e3).tolist()
+    order = sorted(range(live.shape[0]), key=lambda c: lt_[c])
+    tail_ = ((life[:, 1] - life[:, 3]).float() / 1e3).tolist()  # last unit handed over -> exit (drain, epilogue, fix-up)
+    print("CTA lifetime/tail (us) sorted by lifetime: " + " ".join(f"{c}@sm{int(life[c, 2])}:{lt_[c]:.1f}/{tail_[c]:.1f}" for c in order))
 t = allt[:1024].view(64, 16)
 t0 = t[0, 8].item()
 k = t[63]
