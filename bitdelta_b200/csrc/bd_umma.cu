@@ -241,7 +241,7 @@ struct UmmaArgs {
 // bit 10 = sign stores without the conversion ALU work (wrong results; isolates the tcgen05.st path),
 // bit 8 = half the sign work (only the first 32-K group of every unit is unpacked, stored and multiplied: wrong results, the
 // cost profile of a 4-bit sign operand).
-#ifdef BD_BRINGUP
+#if defined(BD_BRINGUP) && !defined(BD_NO_KNOBS)  // (-DBD_NO_KNOBS: the trace without the knobs = the release kernel, traced)
 __device__ __forceinline__ int dbg_flags(const UmmaArgs& a) { return a.dbg; }
 #else
 __device__ __forceinline__ constexpr int dbg_flags(const UmmaArgs&) { return 0; }
@@ -259,9 +259,10 @@ __device__ __forceinline__ void store_y(T16* y, int64_t idx, float v, int fp32) 
 }
 __device__ __forceinline__ int cta_unit_begin(const UmmaArgs& a, int c) { return a.unit_quantum * (c * a.units_per_cta + min(c, a.units_rem)); }
 
-// Hardware named barriers (ids 0..15): far cheaper than mbarriers.  id 0 = __syncthreads, 1 = epilogue, 2 = release of the
-// unpack group, kBarAFull0 + b = "A buffer b is written" (unpack warps + permute warp arrive, the MMA warp syncs).
+// Hardware named barriers (ids 0..15): far cheaper than mbarriers.  id 0 = __syncthreads, 1 = split-K fix-up, 2 = accumulators
+// read out, kBarAFull0 + b = "A buffer b is written" (unpack warps + permute warp arrive, the MMA warp syncs).
 constexpr int kBarAFull0 = 4;
+constexpr int kBarDEmpty = 2;     // unpack warps arrive after reading a run's accumulators, the MMA warp syncs before the next run
 constexpr int kBarTmemReady = 3;  // every warp but the TMA producer: tensor memory allocated, activation tiles zeroed
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -714,6 +715,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       // implies that the stage has landed: those warps only get there after the stage's mbarrier completed.  mbarrier
       // operations are slow and serialised per SM, so every role touches as few of them as it can.
       named_bar_sync(kBarAFull0 + ab.idx, afull_threads);
+      if (seg_first && u != u_begin) named_bar_sync(kBarDEmpty, kUnpackWarps * 32 + 32);  // previous run's accumulators read out
       tc_fence_after();
       Ring st_next = st;
       st_next.advance(a.stages);
@@ -856,6 +858,8 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       }
     };
     bool seg_is_first = true;  // the current (tile, K run) is the first one of this CTA
+    bool pend_valid = false, pend_full = false, pend_first = false;  // run whose read-out is deferred by one round
+    int pend_tile = 0, pend_nt = 0, pend_mc = 0;
     uint32_t dphase = 0;
     // Sign words of one unit -> +-1.0 operand registers -> TMEM A buffer `abi` (this warp's tenants, this thread's row).
     auto unpack_unit = [&](const uint8_t* sp, int abi, int tfirst, int tstep) {
@@ -922,6 +926,203 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         }
       }
     };
+    // Read-out of one (tile, K run): accumulators -> y (whole K) or -> this CTA's split-K slot + fix-up.  `e_next`: another run
+    // follows, the MMA warp waits for these warps to have read the accumulators before it overwrites them (kBarDEmpty).
+    auto read_out = [&](int e_tile, int e_nt, int e_mc, bool e_full, bool e_first, bool e_next) {
+      if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 2] = clock64();
+      // ===================================================== read-out of one (tile, K run)
+      mbar_wait(&bar_dfull, dphase);
+      dphase ^= 1u;
+      tc_fence_after();
+      // which matrix of a grouped launch this tile belongs to
+      const int sg = (e_nt >= a.seg_tile0[1]) + (e_nt >= a.seg_tile0[2]);
+      // row chunk of a prefill-size launch: rows [mc*m, mc*m + m_here) of tenant tt (tt = 0 unless it is a multi-tenant prefill)
+      const int tt = e_nt / a.tpt;
+      const int ltile = e_nt - a.seg_tile0[sg] - tt * a.tpt;
+      const int r_off = tt * a.m_total + e_mc * a.m;
+      const int m_here = min(a.m, a.m_total - e_mc * a.m);
+      const int64_t seg_n = a.n_seg[sg];
+      T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
+      const void* seg_coeff = a.coeff_seg[sg];
+      const int64_t n = (int64_t)ltile * kTileN + row;
+      // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run
+      // of a CTA can be partial; the runs in between cover whole tiles)
+      const int slot = e_first ? 0 : 1;
+      float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
+
+      if constexpr (DELTA8) {
+        // delta accumulator: 8 columns per tenant (one row per tenant), columns 0..2 = the three pieces of the scaled
+        // activation; the two warps of a quadrant take alternate tenants
+        for (int t = grp; t < a.T; t += 2) {
+          const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
+          float d0[8], bv = 0.f;
+          tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 8, d0);
+          if (HAS_BASE) bv = tmem_ld1(tmem_base + lane_addr + col_dbase + t);
+          tc_wait_ld();
+          const float dsum = (d0[0] + d0[1] + d0[2] + (kD8Pieces > 3 ? d0[3] : 0.f)) * __uint_as_float((254u - d8_scale_field(t)) << 23);  // undo the row scale
+          const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
+          if (e_full) {
+            if (n < seg_n) store_y(y, (int64_t)t * seg_n + n, v, a.fp32_out);
+          } else {
+            part[(size_t)t * kTileN + row] = v;
+          }
+        }
+      } else
+      for (int t = 0; t < a.T; ++t) {
+        const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t + tt) : 1.0f;
+        for (int c8 = 0; c8 < a.mp / 8; ++c8) {
+          if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
+          if (c8 * 8 >= m_here) continue;
+          float dv[8], bv[8];
+          tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
+          if (HAS_BASE && a.T == 1) {
+            tmem_ld8(tmem_base + lane_addr + col_dbase + c8 * 8, bv);  // one tenant: base columns line up with the chunk
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              bv[i] = 0.f;
+              if (HAS_BASE && c8 * 8 + i < m_here) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
+            }
+          }
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ii = c8 * 8 + i;
+            if (ii >= m_here) continue;
+            const int r = t * a.m + ii;
+            const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
+            if (e_full) {
+              if (n < seg_n) store_y(y, (int64_t)(r_off + r) * seg_n + n, v, a.fp32_out);
+            } else {
+              part[(size_t)r * kTileN + row] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+
+      // every unpack warp has read its part of the accumulators: the MMA warp may start the next run (it waits for all
+      // eight warps here -- with alternating units a unit's hand-over involves only half of them)
+      if (e_next) named_bar_arrive(kBarDEmpty, kUnpackWarps * 32 + 32);
+
+      if (!e_full) {
+        // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
+        const int first_unit = e_tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
+        const int big = a.units_rem * (a.units_per_cta + 1);  // units owned by the CTAs that got one extra unit
+        const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
+        const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+        if (ut == 0) {
+          const unsigned old = atomicAdd(&a.counters[e_tile], 1u);
+          s_is_last = (old == (unsigned)(c_last - c_first)) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+        if (s_is_last) {
+          __threadfence();
+          // Deterministic reduction with memory-level parallelism: work item = (output row r, 4 consecutive weight
+          // rows); the slots of all contributors are fetched with independent 16-byte L2 loads, 8 in flight per
+          // thread, and added in K order.  (A serial loop over ~18 contributors cost a 10 us tail per launch.)
+          const int items = (a.m_chunks > 1 ? m_here : a.rows) * (kTileN / 4);
+          for (int item = ut; item < items; item += kUnpackWarps * 32) {
+            const int r = item / (kTileN / 4), q4 = item - r * (kTileN / 4);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c0 = c_first; c0 <= c_last; c0 += 8) {
+              float4 v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c <= c_last) {
+                  const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
+                  v[j] = __ldcg(reinterpret_cast<const float4*>(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN) + q4);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+            }
+            const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
+            const int64_t o4 = (int64_t)(r_off + r) * seg_n + n4;
+            if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte (fp32: 16-byte) aligned for these 4 elements
+              if (a.fp32_out) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o4) = acc;
+              } else {
+                const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
+                *reinterpret_cast<uint2*>(y + o4) = *reinterpret_cast<const uint2*>(o);
+              }
+            }
+          }
+          if (ut == 0) a.counters[e_tile] = 0u;  // leave the workspace clean for the next launch
+        }
+      }
+      if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 3] = clock64();
+    };
+    if (alt_units) {
+      // ---- decode path: the two warp groups take alternate units.  One warp's whole per-unit loop is: release check,
+      // unpack, store drain, barrier arrive, two ring steps -- the run bookkeeping (tile cursor, read-out) sits outside it:
+      // as straight-line code of one loop it cost these warps ~500 cycles of branches and constant loads per unit.
+      // A run that is followed by another one is read out one unit LATE: these warps first hand over their first unit of
+      // the next run, so that the MMA warp has work ready the moment the accumulators are free, and the run's MMAs have
+      // long completed when these warps come to wait for them (read out right away, every run boundary emptied the
+      // pipeline: CTAs with two runs finished ~3 us after those with one).
+      const int n_units = u_end - u_begin;
+      int it = grp;                       // this warp's next unit (CTA-relative): grp, grp + 2, ...
+      int sti = grp, abi = grp;           // its stage / A buffer (stages, n_abuf >= 2)
+      if (sti >= a.stages) sti -= a.stages;
+      if (abi >= a.n_abuf) abi -= a.n_abuf;
+      auto own_unit = [&]() {
+        if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 0);
+        wait_released<BD_UNPACK_SLEEP>(&s_released, it);
+        tc_fence_after();
+        if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 1);
+        if (!(dbg_flags(a) & 1)) {
+          unpack_unit(smem + (size_t)sti * a.stage_bytes, abi, 0, 1);
+          if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 3);
+          tc_wait_st();
+        }
+        tc_fence_before();
+        if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 4);
+        named_bar_arrive(kBarAFull0 + abi, afull_threads);  // this warp's rows of A buffer abi are written
+        if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 11);
+        sti += 2; if (sti >= a.stages) sti -= a.stages;
+        abi += 2; if (abi >= a.n_abuf) abi -= a.n_abuf;
+        if (uw == 0 && lane == 0) trace_mark<TRACE>(a, it, 13);
+        it += 2;
+      };
+      int rb = 0;                         // CTA-relative first unit of the current run
+      bool more = n_units > 0, pend_next = false;
+      int re = 0;
+      while (true) {
+        if (more) {
+          re = min(n_units, rb + a.kblocks - kb);
+          if (it < re) own_unit();        // first own unit of the run: ahead of the previous run's read-out
+        }
+        if (pend_valid) {
+          if (TRACE && a.trace != nullptr && threadIdx.x == 0 && !pend_next) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(a.trace[1024 + 4 * blockIdx.x + 3]));  // last unit handed over
+          if (dbg_flags(a) & 1) {  // bring-up: stream only
+            mbar_wait(&bar_dfull, dphase);
+            dphase ^= 1u;
+            if (pend_next) named_bar_arrive(kBarDEmpty, kUnpackWarps * 32 + 32);
+          } else {
+            read_out(pend_tile, pend_nt, pend_mc, pend_full, pend_first, pend_next);
+          }
+          pend_valid = false;
+        }
+        if (!more) break;
+#pragma unroll 1
+        while (it < re) own_unit();
+        // the run [rb, re) is handed over: remember it for the read-out, step to the next tile
+        pend_valid = true; pend_tile = tile; pend_nt = nt; pend_mc = mc;
+        pend_full = (kb == 0) && (kb + (re - rb) == a.kblocks);
+        pend_first = (rb == 0);
+        pend_next = (re < n_units);
+        kb += re - rb;
+        if (kb == a.kblocks) { kb = 0; advance_tile(); }
+        rb = re;
+        more = rb < n_units;
+      }
+    } else {
+    // ---- prefill-size row counts and the 16-bit operand path: the two warps of a quadrant split every unit's tenants.
     // Units are processed in rounds of up to two (never across the end of a (tile, K run)): the per-round costs of this
     // in-order warp -- release check, tcgen05 fences, tcgen05.wait::st, loop bookkeeping, ~800 cycles -- are paid once per
     // round instead of once per unit.  Two rounds fit the >= 4 A buffers, so unpacking still overlaps with the MMAs.
@@ -935,30 +1136,6 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       const bool tr = (uw == 0 && lane == 0);
       // The sync warp waits on the mbarriers for the whole group and publishes released units in s_released.
       if (tr) trace_mark<TRACE>(a, it, 0);
-      if (alt_units) {
-        // this warp's unit of the round (at most one: g <= 2): the one whose index has this warp group's parity
-        const int my = ((it & 1) == grp) ? 0 : 1;
-        if (my < g) {
-          wait_released<BD_UNPACK_SLEEP>(&s_released, it + my);
-          tc_fence_after();
-          if (tr) trace_mark<TRACE>(a, it, 1);
-          Ring st_i = st, ab_i = ab;
-          if (my) { st_i.advance(a.stages); ab_i.advance(a.n_abuf); }
-          if (!(dbg_flags(a) & 1)) {
-            unpack_unit(smem + (size_t)st_i.idx * a.stage_bytes, ab_i.idx, 0, 1);
-            if (tr) trace_mark<TRACE>(a, it, 3);
-            tc_wait_st();
-          }
-          tc_fence_before();
-          if (tr) trace_mark<TRACE>(a, it, 4);
-          named_bar_arrive(kBarAFull0 + ab_i.idx, afull_threads);  // this warp's rows of A buffer ab_i.idx are written
-          if (tr) trace_mark<TRACE>(a, it, 11);
-        }
-        // (closed form, g <= 2 <= ring sizes: the generic per-step loop compiled into a long chain of branches that cost this
-        // warp ~10 % of its time; these warps only use the ring indices, not the phases)
-        st.idx += g; if (st.idx >= a.stages) st.idx -= a.stages;
-        ab.idx += g; if (ab.idx >= a.n_abuf) ab.idx -= a.n_abuf;
-      } else {
       wait_released(&s_released, it + g - 1);
       tc_fence_after();
       if (tr) trace_mark<TRACE>(a, it, 1);
@@ -987,13 +1164,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         ab.advance(a.n_abuf);
       }
       if (tr) trace_mark<TRACE>(a, it, 11);
-      }
       if (tr) trace_mark<TRACE>(a, it, 12);
       u += g;
       kb += g - 1;  // kb = K block of the last unit of the round (the epilogue below looks at it)
       if ((dbg_flags(a) & 1) && seg_last) {
         mbar_wait(&bar_dfull, dphase);
         dphase ^= 1u;
+        if (u < u_end) named_bar_arrive(kBarDEmpty, kUnpackWarps * 32 + 32);
         if (++kb == a.kblocks) { kb = 0; advance_tile(); }
         seg_kb0 = kb;
         seg_is_first = false;
@@ -1001,141 +1178,14 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
       }
 
       if (seg_last) {
-        if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 2] = clock64();
         if (TRACE && a.trace != nullptr && threadIdx.x == 0 && u == u_end) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(a.trace[1024 + 4 * blockIdx.x + 3]));  // last unit handed over
-        // ===================================================== epilogue of this (tile, K run)
-        mbar_wait(&bar_dfull, dphase);
-        dphase ^= 1u;
-        tc_fence_after();
-        const bool full_k = (seg_kb0 == 0) && (kb + 1 == a.kblocks);
-        // which matrix of a grouped launch this tile belongs to
-        const int sg = (nt >= a.seg_tile0[1]) + (nt >= a.seg_tile0[2]);
-        // row chunk of a prefill-size launch: rows [mc*m, mc*m + m_here) of tenant tt (tt = 0 unless it is a multi-tenant prefill)
-        const int tt = nt / a.tpt;
-        const int ltile = nt - a.seg_tile0[sg] - tt * a.tpt;
-        const int r_off = tt * a.m_total + mc * a.m;
-        const int m_here = min(a.m, a.m_total - mc * a.m);
-        const int64_t seg_n = a.n_seg[sg];
-        T16* __restrict__ y = reinterpret_cast<T16*>(a.y_seg[sg]);
-        const void* seg_coeff = a.coeff_seg[sg];
-        const int64_t n = (int64_t)ltile * kTileN + row;
-        // this CTA's partial slot: 0 if the run starts the CTA's unit range, else 1 (only the first and the last run
-        // of a CTA can be partial; the runs in between cover whole tiles)
-        const int slot = seg_is_first ? 0 : 1;
-        float* part = a.partial + ((size_t)(cta * 2 + slot) * a.rows) * kTileN;
-
-        if constexpr (DELTA8) {
-          // delta accumulator: 8 columns per tenant (one row per tenant), columns 0..2 = the three pieces of the scaled
-          // activation; the two warps of a quadrant take alternate tenants
-          for (int t = grp; t < a.T; t += 2) {
-            const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t) : 1.0f;
-            float d0[8], bv = 0.f;
-            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * 8, d0);
-            if (HAS_BASE) bv = tmem_ld1(tmem_base + lane_addr + col_dbase + t);
-            tc_wait_ld();
-            const float dsum = (d0[0] + d0[1] + d0[2] + (kD8Pieces > 3 ? d0[3] : 0.f)) * __uint_as_float((254u - d8_scale_field(t)) << 23);  // undo the row scale
-            const float v = HAS_BASE ? fmaf(cf, dsum, bv) : dsum;
-            if (full_k) {
-              if (n < seg_n) store_y(y, (int64_t)t * seg_n + n, v, a.fp32_out);
-            } else {
-              part[(size_t)t * kTileN + row] = v;
-            }
-          }
-        } else
-        for (int t = 0; t < a.T; ++t) {
-          const float cf = HAS_BASE ? load_coeff(seg_coeff, a.coeff_dtype, t + tt) : 1.0f;
-          for (int c8 = 0; c8 < a.mp / 8; ++c8) {
-            if (((t * (a.mp / 8) + c8) & 1) != grp) continue;   // the two warps of a quadrant split the column chunks
-            if (c8 * 8 >= m_here) continue;
-            float dv[8], bv[8];
-            tmem_ld8(tmem_base + lane_addr + col_ddelta + t * a.mp + c8 * 8, dv);
-            if (HAS_BASE && a.T == 1) {
-              tmem_ld8(tmem_base + lane_addr + col_dbase + c8 * 8, bv);  // one tenant: base columns line up with the chunk
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                bv[i] = 0.f;
-                if (HAS_BASE && c8 * 8 + i < m_here) bv[i] = tmem_ld1(tmem_base + lane_addr + col_dbase + t * a.m + c8 * 8 + i);
-              }
-            }
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ii = c8 * 8 + i;
-              if (ii >= m_here) continue;
-              const int r = t * a.m + ii;
-              const float v = HAS_BASE ? fmaf(cf, dv[i], bv[i]) : dv[i];
-              if (full_k) {
-                if (n < seg_n) store_y(y, (int64_t)(r_off + r) * seg_n + n, v, a.fp32_out);
-              } else {
-                part[(size_t)r * kTileN + row] = v;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-
-        if (full_k) {
-          // every unpack warp has read its part of the accumulators: only now may any of them hand the MMA warp the first
-          // unit of the next run (with alternating units that hand-over involves only half of these warps; the split-K
-          // branch below has its own barriers)
-          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-        } else {
-          // ---- split-K fix-up: the last CTA to arrive sums every contributor's slot in K order ----
-          const int first_unit = tile * a.kblocks, last_unit = first_unit + a.kblocks - 1;
-          const int big = a.units_rem * (a.units_per_cta + 1);  // units owned by the CTAs that got one extra unit
-          const int c_first = first_unit < big ? first_unit / (a.units_per_cta + 1) : a.units_rem + (first_unit - big) / a.units_per_cta;
-          const int c_last = last_unit < big ? last_unit / (a.units_per_cta + 1) : a.units_rem + (last_unit - big) / a.units_per_cta;
-          __threadfence();
-          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-          if (ut == 0) {
-            const unsigned old = atomicAdd(&a.counters[tile], 1u);
-            s_is_last = (old == (unsigned)(c_last - c_first)) ? 1u : 0u;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
-          if (s_is_last) {
-            __threadfence();
-            // Deterministic reduction with memory-level parallelism: work item = (output row r, 4 consecutive weight
-            // rows); the slots of all contributors are fetched with independent 16-byte L2 loads, 8 in flight per
-            // thread, and added in K order.  (A serial loop over ~18 contributors cost a 10 us tail per launch.)
-            const int items = (a.m_chunks > 1 ? m_here : a.rows) * (kTileN / 4);
-            for (int item = ut; item < items; item += kUnpackWarps * 32) {
-              const int r = item / (kTileN / 4), q4 = item - r * (kTileN / 4);
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int c0 = c_first; c0 <= c_last; c0 += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int c = c0 + j;
-                  v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (c <= c_last) {
-                    const int cs = (cta_unit_begin(a, c) >= first_unit) ? 0 : 1;
-                    v[j] = __ldcg(reinterpret_cast<const float4*>(a.partial + ((size_t)(c * 2 + cs) * a.rows + r) * kTileN) + q4);
-                  }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-              }
-              const int64_t n4 = (int64_t)ltile * kTileN + q4 * 4;
-              const int64_t o4 = (int64_t)(r_off + r) * seg_n + n4;
-              if (n4 + 3 < seg_n) {  // N % 4 == 0 and rows of y are 8-byte (fp32: 16-byte) aligned for these 4 elements
-                if (a.fp32_out) {
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o4) = acc;
-                } else {
-                  const T16 o[4] = {F16<T16>::from_f32(acc.x), F16<T16>::from_f32(acc.y), F16<T16>::from_f32(acc.z), F16<T16>::from_f32(acc.w)};
-                  *reinterpret_cast<uint2*>(y + o4) = *reinterpret_cast<const uint2*>(o);
-                }
-              }
-            }
-            if (ut == 0) a.counters[tile] = 0u;  // leave the workspace clean for the next launch
-          }
-        }
+        read_out(tile, nt, mc, (seg_kb0 == 0) && (kb + 1 == a.kblocks), seg_is_first, u < u_end);
         seg_is_first = false;
-        if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.trace[63 * 16 + 3] = clock64();
       }
       if (++kb == a.kblocks) { kb = 0; advance_tile(); }
       if (seg_last) seg_kb0 = kb;  // the next run starts at the next unit (kb == 0 unless the CTA's range ended)
       if (tr) trace_mark<TRACE>(a, it, 13);
+    }
     }
   }
 
