@@ -151,6 +151,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_smem) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem) : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -704,10 +707,65 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     const uint32_t w_lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4, stage_lo = a.stage_bytes >> 4;
     const uint32_t x_off_lo = a.off_x >> 4;
     const uint32_t xp_lo0 = (smem_u32(smem + a.off_xp) & 0x3FFFFu) >> 4, xp_buf_lo = a.xp_buf_bytes >> 4, xp_t_lo = DELTA8 ? (512u >> 4) : (uint32_t)a.mp * 8;
+    // 8-bit path, common tenant counts: the whole loop is specialised on the tenant count and keeps everything a unit needs
+    // (descriptor bases, barrier addresses, ring positions) in registers, stepped incrementally.  With the unpack warps out
+    // of the way this ONE thread paces the kernel -- per unit its MMAs occupy the tensor pipe for ~37 cycles each and
+    // everything else it executes between two units (barrier, commits, loop) adds on top, because the pipe's issue queue
+    // is only a few MMAs deep.
+    bool fast_done = false;
+    if constexpr (DELTA8) {
+      auto fast_loop = [&](auto ttc) {
+        constexpr int TT = decltype(ttc)::value;
+        uint32_t n_stages = a.stages, n_abuf = a.n_abuf, kblocks = a.kblocks, aft = afull_threads;
+        asm volatile("" : "+r"(n_stages), "+r"(n_abuf), "+r"(kblocks), "+r"(aft));  // loop invariants: registers, not constant-bank reloads
+        const uint32_t empty0 = smem_u32(&bar_empty[0]), aempty0 = smem_u32(&bar_aempty[0]), dfull_addr = smem_u32(&bar_dfull);
+        const uint32_t d_base = tmem_base + col_dbase, d_delta = tmem_base + col_ddelta, a_tmem00 = tmem_base + col_abuf0;
+        const uint32_t bl00 = xp_lo0 | kDesc8LoLbo;
+        uint32_t sti = 0, abi = 0, kb = kb0;
+        uint32_t w_lo = w_lo0, bl0 = bl00, a_tmem0 = a_tmem00;
+        uint32_t bar_e = empty0, bar_a = aempty0;
+        int left = u_end - u_begin;
+        bool first = true;
+#pragma unroll 1
+        for (; left > 0; --left) {
+          const bool seg_first = first || kb == 0;
+          const bool seg_last = left == 1 || kb + 1 == kblocks;
+          if (lane == 0) trace_mark<TRACE>(a, (u_end - u_begin) - left, 5);
+          named_bar_sync(kBarAFull0 + abi, aft);
+          if (seg_first && !first) named_bar_sync(kBarDEmpty, kUnpackWarps * 32 + 32);  // previous run's accumulators read out
+          tc_fence_after();
+          if (leader) {
+            trace_mark<TRACE>(a, (u_end - u_begin) - left, 6);
+            issue_unit_d8<TT, HAS_BASE>(d_base, d_delta, w_lo, w_lo + x_off_lo, a_tmem0, bl0, idesc_base, idesc_delta, seg_first ? 0u : 1u);
+            tc_commit_addr(bar_e);   // stage (W tile, masks, X tile) may be overwritten once these MMAs retire
+            tc_commit_addr(bar_a);   // so may the TMEM A buffer and its permuted-X tiles
+            if (seg_last) tc_commit_addr(dfull_addr);
+            trace_mark<TRACE>(a, (u_end - u_begin) - left, 7);
+          }
+          __syncwarp();
+          first = false;
+          if (++sti == n_stages) { sti = 0; w_lo = w_lo0; bar_e = empty0; } else { w_lo += stage_lo; bar_e += 8; }
+          if (++abi == n_abuf) { abi = 0; bl0 = bl00; a_tmem0 = a_tmem00; bar_a = aempty0; } else { bl0 += xp_buf_lo; a_tmem0 += a_cols_per_buf; bar_a += 8; }
+          if (++kb == kblocks) kb = 0;
+        }
+      };
+      if (dbg_flags(a) == 0) {
+        fast_done = true;
+        switch (a.T) {
+          case 1: fast_loop(std::integral_constant<int, 1>{}); break;
+          case 2: fast_loop(std::integral_constant<int, 2>{}); break;
+          case 3: fast_loop(std::integral_constant<int, 3>{}); break;
+          case 4: fast_loop(std::integral_constant<int, 4>{}); break;
+          case 6: fast_loop(std::integral_constant<int, 6>{}); break;
+          case 8: fast_loop(std::integral_constant<int, 8>{}); break;
+          default: fast_done = false; break;  // other tenant counts: the generic loop below
+        }
+      }
+    }
     Ring st, ab;
     int kb = kb0;
 #pragma unroll 1
-    for (int u = u_begin; u < u_end; ++u) {
+    for (int u = fast_done ? u_end : u_begin; u < u_end; ++u) {
       const bool seg_first = (u == u_begin) || (kb == 0);
       const bool seg_last = (u + 1 == u_end) || (kb + 1 == a.kblocks);
       if (lane == 0) trace_mark<TRACE>(a, u - u_begin, 5);
@@ -728,23 +786,6 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         const uint32_t a_tmem0 = tmem_base + col_abuf0 + ab.idx * a_cols_per_buf;
         const uint32_t d_base = tmem_base + col_dbase, d_delta = tmem_base + col_ddelta;
         // k-step outermost: consecutive MMAs go to different accumulators (base, tenant 0, tenant 1, ...)
-        bool issued = false;
-        if constexpr (DELTA8) {
-          if (!(dbg_flags(a) & 256)) {
-            const uint32_t acc0 = seg_first ? 0u : 1u, bl0 = xp_lo | kDesc8LoLbo;
-            issued = true;
-            switch (a.T) {
-              case 1: issue_unit_d8<1, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              case 2: issue_unit_d8<2, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              case 3: issue_unit_d8<3, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              case 4: issue_unit_d8<4, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              case 6: issue_unit_d8<6, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              case 8: issue_unit_d8<8, HAS_BASE>(d_base, d_delta, w_lo, x_lo, a_tmem0, bl0, idesc_base, idesc_delta, acc0); break;
-              default: issued = false; break;  // other tenant counts: the generic loop below
-            }
-          }
-        }
-        if (!issued)
 #pragma unroll
         for (int ks = 0; ks < kBlockK / 16; ++ks) {
           const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
