@@ -95,6 +95,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -414,7 +417,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles and their UMMA descriptors need 1024-byte alignment: align by hand (the host adds 1 KiB of slack)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_aempty[kMaxABuf], bar_dfull;
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_dfull;
   __shared__ uint32_t tmem_base_slot;
   __shared__ unsigned s_is_last;
   __shared__ int s_released;  // number of units the sync warp has released to the unpack group (release/acquire)
@@ -459,13 +462,16 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // prefetches the tensor maps
     if (lane < kMaxStages) {
       if (lane < a.stages) {
-        mbar_init(&bar_full[lane], 1);
+        // "unit u may be unpacked" = its stage has landed AND the A buffer it will use is free.  Both events arrive on the
+        // SAME barrier: the producer's arrive.expect_tx (+ the TMA bytes) and the MMA commit of unit u - n_abuf, which
+        // targets the stage of unit u (n_abuf <= stages, so that stage's previous phase is long complete).  One mbarrier
+        // wait per unit instead of two: mbarrier operations cost the sync warp ~300 cycles each and it paces the kernel.
+        mbar_init(&bar_full[lane], 2);
+        if (lane < a.n_abuf) mbar_arrive(&bar_full[lane]);  // the first n_abuf units find their A buffer free
         // A stage is released by the MMA commit alone: the MMAs of a unit are issued only after every unpack warp and
         // the permute warp have arrived on bar_afull, i.e. after they are done reading the stage.
         mbar_init(&bar_empty[lane], 1);
       }
-    } else if (lane < kMaxStages + kMaxABuf) {
-      if (lane - kMaxStages < a.n_abuf) mbar_init(&bar_aempty[lane - kMaxStages], 1);
     } else if (lane == kMaxStages + kMaxABuf) {
       mbar_init(&bar_dfull, 1);
     } else if (lane == 31) {
@@ -718,12 +724,13 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         constexpr int TT = decltype(ttc)::value;
         uint32_t n_stages = a.stages, n_abuf = a.n_abuf, kblocks = a.kblocks, aft = afull_threads;
         asm volatile("" : "+r"(n_stages), "+r"(n_abuf), "+r"(kblocks), "+r"(aft));  // loop invariants: registers, not constant-bank reloads
-        const uint32_t empty0 = smem_u32(&bar_empty[0]), aempty0 = smem_u32(&bar_aempty[0]), dfull_addr = smem_u32(&bar_dfull);
+        const uint32_t empty0 = smem_u32(&bar_empty[0]), full0 = smem_u32(&bar_full[0]), dfull_addr = smem_u32(&bar_dfull);
         const uint32_t d_base = tmem_base + col_dbase, d_delta = tmem_base + col_ddelta, a_tmem00 = tmem_base + col_abuf0;
         const uint32_t bl00 = xp_lo0 | kDesc8LoLbo;
         uint32_t sti = 0, abi = 0, kb = kb0;
         uint32_t w_lo = w_lo0, bl0 = bl00, a_tmem0 = a_tmem00;
-        uint32_t bar_e = empty0, bar_a = aempty0;
+        uint32_t ati = n_abuf == n_stages ? 0u : n_abuf;  // stage of unit u + n_abuf, the next user of this unit's A buffer
+        uint32_t bar_e = empty0, bar_a = full0 + 8 * ati;
         int left = u_end - u_begin;
         bool first = true;
 #pragma unroll 1
@@ -738,14 +745,15 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
             trace_mark<TRACE>(a, (u_end - u_begin) - left, 6);
             issue_unit_d8<TT, HAS_BASE>(d_base, d_delta, w_lo, w_lo + x_off_lo, a_tmem0, bl0, idesc_base, idesc_delta, seg_first ? 0u : 1u);
             tc_commit_addr(bar_e);   // stage (W tile, masks, X tile) may be overwritten once these MMAs retire
-            tc_commit_addr(bar_a);   // so may the TMEM A buffer and its permuted-X tiles
+            tc_commit_addr(bar_a);   // so may the TMEM A buffer and its permuted-X tiles: second arrival of unit u + n_abuf's barrier
             if (seg_last) tc_commit_addr(dfull_addr);
             trace_mark<TRACE>(a, (u_end - u_begin) - left, 7);
           }
           __syncwarp();
           first = false;
           if (++sti == n_stages) { sti = 0; w_lo = w_lo0; bar_e = empty0; } else { w_lo += stage_lo; bar_e += 8; }
-          if (++abi == n_abuf) { abi = 0; bl0 = bl00; a_tmem0 = a_tmem00; bar_a = aempty0; } else { bl0 += xp_buf_lo; a_tmem0 += a_cols_per_buf; bar_a += 8; }
+          if (++abi == n_abuf) { abi = 0; bl0 = bl00; a_tmem0 = a_tmem00; } else { bl0 += xp_buf_lo; a_tmem0 += a_cols_per_buf; }
+          if (++ati == n_stages) { ati = 0; bar_a = full0; } else { bar_a += 8; }
           if (++kb == kblocks) kb = 0;
         }
       };
@@ -812,7 +820,11 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         }
         }
         tc_commit(&bar_empty[st.idx]);   // stage (W tile, masks, X tile) may be overwritten once these MMAs retire
-        tc_commit(&bar_aempty[ab.idx]);  // so may the TMEM A buffer and its permuted-X tiles
+        {  // so may the TMEM A buffer and its permuted-X tiles: second arrival on the barrier of unit u + n_abuf (see the set-up)
+          int nxt = st.idx + a.n_abuf;
+          if (nxt >= a.stages) nxt -= a.stages;
+          tc_commit(&bar_full[nxt]);
+        }
         if (seg_last) tc_commit(&bar_dfull);
         trace_mark<TRACE>(a, u - u_begin, 7);
       }
@@ -863,17 +875,14 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     // The only warp of the unpack group that talks to the mbarriers (they are slow and serialised per SM): waits until
     // the stage has landed and an A buffer is free, then publishes the unit in a shared-memory counter (release store;
     // the unpack and permute warps acquire-load it).  It runs ahead of them, so they normally never wait.
-    Ring st, ab;
+    Ring st;
 #pragma unroll 1
     for (int u = u_begin; u < u_end; ++u) {
-      mbar_wait(&bar_full[st.idx], st.phase);
-      if (lane == 0) trace_mark<TRACE>(a, u - u_begin, 14);
-      mbar_wait(&bar_aempty[ab.idx], ab.phase ^ 1u);
+      mbar_wait(&bar_full[st.idx], st.phase);  // stage landed + A buffer free (both arrive on this barrier)
       if (lane == 0) trace_mark<TRACE>(a, u - u_begin, 15);
       __syncwarp();
       if (lane == 0) st_release_shared(&s_released, u - u_begin + 1);
       st.advance(a.stages);
-      ab.advance(a.n_abuf);
     }
   } else {
     // ===================================================== unpack + epilogue warps
@@ -1327,6 +1336,9 @@ UmmaPlan plan_umma(int64_t T, int64_t m, int64_t K, int64_t N, bool has_base, bo
   if (fixed + 3 * p.stage_bytes > budget) { p.why = "tile does not fit in shared memory"; return p; }
   p.stages = (int)((budget - fixed) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  // An A buffer is held for a sub-interval of its unit's stage, so more A buffers than stages buy nothing -- and the kernel
+  // relies on n_abuf <= stages (the MMA commit of unit u arrives on the stage barrier of unit u + n_abuf).
+  if (p.n_abuf > p.stages) p.n_abuf = p.stages;
   p.off_xp = p.stages * p.stage_bytes;
   p.smem_bytes = p.off_xp + fixed + 1024;  // + slack for the manual 1 KiB alignment
   p.ok = true;
