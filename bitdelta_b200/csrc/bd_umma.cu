@@ -739,17 +739,20 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
           const bool seg_last = left == 1 || kb + 1 == kblocks;
           if (lane == 0) trace_mark<TRACE>(a, (u_end - u_begin) - left, 5);
           named_bar_sync(kBarAFull0 + abi, aft);
+          if (lane == 0) trace_mark<TRACE>(a, (u_end - u_begin) - left, 2);
           if (seg_first && !first) named_bar_sync(kBarDEmpty, kUnpackWarps * 32 + 32);  // previous run's accumulators read out
           tc_fence_after();
           if (leader) {
             trace_mark<TRACE>(a, (u_end - u_begin) - left, 6);
             issue_unit_d8<TT, HAS_BASE>(d_base, d_delta, w_lo, w_lo + x_off_lo, a_tmem0, bl0, idesc_base, idesc_delta, seg_first ? 0u : 1u);
+            trace_mark<TRACE>(a, (u_end - u_begin) - left, 9);
             tc_commit_addr(bar_e);   // stage (W tile, masks, X tile) may be overwritten once these MMAs retire
             tc_commit_addr(bar_a);   // so may the TMEM A buffer and its permuted-X tiles: second arrival of unit u + n_abuf's barrier
             if (seg_last) tc_commit_addr(dfull_addr);
             trace_mark<TRACE>(a, (u_end - u_begin) - left, 7);
           }
           __syncwarp();
+          if (lane == 0) trace_mark<TRACE>(a, (u_end - u_begin) - left, 12);
           first = false;
           if (++sti == n_stages) { sti = 0; w_lo = w_lo0; bar_e = empty0; } else { w_lo += stage_lo; bar_e += 8; }
           if (++abi == n_abuf) { abi = 0; bl0 = bl00; a_tmem0 = a_tmem00; } else { bl0 += xp_buf_lo; a_tmem0 += a_cols_per_buf; }

@@ -43,7 +43,7 @@ t = allt[:1024].view(64, 16)
 t0 = t[0, 8].item()
 k = t[63]
 print(f"kernel (CTA 0): entry->setup {k[1]-k[0]} cyc, setup->first TMA {t0-k[1]}, first TMA->last unit done {k[2]-t0}, last epilogue {k[3]-k[2]}, ->teardown {k[4]-k[3]}; total {k[4]-k[0]} cyc = {(k[9]-k[8])/1e3:.2f} us (globaltimer)")
-names = ["U:full", "U:aempty", "U:xperm", "U:unpk", "U:fenced", "M:full", "M:afull", "M:issued", "P:empty", "U7:fenced", "X:done", "U:arrived", "U:s12", "U:s13", "S:full", "S:aempty"]
+names = ["U:start", "U:released", "M:synced", "U:unpk", "U:fenced", "M:top", "M:fenced", "M:commit", "P:empty", "M:issued", "X:done", "U:arrived", "M:conv", "U:end", "S:full", "S:release"]
 rows = [[t[it, s_].item() for s_ in range(14)] for it in range(8, 56) if t[it, 1].item() and t[it + 2, 0].item()]
 if rows:
     import statistics as st_
