@@ -467,7 +467,6 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
         // targets the stage of unit u (n_abuf <= stages, so that stage's previous phase is long complete).  One mbarrier
         // wait per unit instead of two: mbarrier operations cost the sync warp ~300 cycles each and it paces the kernel.
         mbar_init(&bar_full[lane], 2);
-        if (lane < a.n_abuf) mbar_arrive(&bar_full[lane]);  // the first n_abuf units find their A buffer free
         // A stage is released by the MMA commit alone: the MMAs of a unit are issued only after every unpack warp and
         // the permute warp have arrived on bar_afull, i.e. after they are done reading the stage.
         mbar_init(&bar_empty[lane], 1);
@@ -483,6 +482,7 @@ fwd_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaArgs a) {
     }
     fence_barrier_init();
     __syncwarp();  // lane 0 (the TMA producer) uses barriers its sibling lanes initialised
+    if (lane < a.n_abuf) mbar_arrive(&bar_full[lane]);  // the first n_abuf units find their A buffer free (n_abuf <= stages)
   }
   if (threadIdx.x == 0) s_released = 0;
   if (DELTA8 && threadIdx.x < kD8MaxTenants) s_rowexp[threadIdx.x] = 0;
