@@ -610,6 +610,28 @@ def test_mistral_shapes_six_tenants(kernel, N, K, m, T):
     assert np.allclose(exact[:, :, sl].cpu().numpy(), ex_o, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("N,K,T", [(40000, 64, 6), (30000, 128, 1), (19000, 192, 6), (9000, 320, 3), (33000, 512, 8), (32000, 4096, 6)])
+def test_decode_many_runs_per_cta(N, K, T):
+    # Short K against many weight-row tiles: every CTA of the tcgen05 kernel works through several (tile, K run)s -- runs of
+    # ONE unit (K = 64: a warp group then has no unit of its own in every other run), whole-tile runs in the middle of a
+    # CTA's range, partial runs at both ends.  Exercises the deferred read-out (next run's first unit handed over before
+    # the previous run's accumulators are read) and the accumulators-read handshake with the MMA warp at every boundary.
+    gen = torch.Generator(device=DEV).manual_seed(N + K + T)
+    w = (torch.randn(N, K, generator=gen, device=DEV) * 0.05).bfloat16()
+    masks = torch.randint(-(2**31), 2**31 - 1, (T, K // 32, N), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    coeffs = (torch.rand(T, generator=gen, device=DEV) * 0.01 + 0.001).bfloat16()
+    x = torch.randn(T, 1, K, generator=gen, device=DEV).bfloat16()
+    lin = torch.nn.Linear(K, N, bias=False, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mod = bd.DiffCompressModule(lin, masks, coeffs)
+    mod.kernel = "umma"
+    signs = bd.unpack(masks).double() * 2 - 1
+    exact = (x.double() @ w.double().T + coeffs.double()[:, None, None] * torch.bmm(x.double(), signs)).cpu().numpy()
+    for rep in range(3):  # back to back: the workspace (arrival counters, slots) left by one launch serves the next
+        assert_close_to_exact(mod(x), exact, f"many runs {N}x{K} T={T} launch {rep}")
+
+
 @pytest.mark.parametrize("shapes,T,m", [([4096, 1024, 1024], 6, 1), ([14336, 14336], 6, 1), ([256, 384, 200], 3, 2), ([1024, 1024], 8, 1)])
 def test_grouped_launch_matches_individual_modules(shapes, T, m):
     # q/k/v and gate/up called back to back on the same input share ONE launch (SiblingGroup); results must match the
