@@ -610,7 +610,8 @@ def test_mistral_shapes_six_tenants(kernel, N, K, m, T):
     assert np.allclose(exact[:, :, sl].cpu().numpy(), ex_o, rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("N,K,T", [(40000, 64, 6), (30000, 128, 1), (19000, 192, 6), (9000, 320, 3), (33000, 512, 8), (32000, 4096, 6)])
+@pytest.mark.parametrize("N,K,T", [(40000, 64, 6), (30000, 128, 1), (19000, 192, 6), (9000, 320, 3), (33000, 512, 8), (32000, 4096, 6),
+                                   (20000, 256, 5), (6000, 1024, 7), (12000, 512, 10), (3000, 2048, 2), (5000, 768, 4)])  # T = 5, 7, 10: the MMA issuer's generic loop
 def test_decode_many_runs_per_cta(N, K, T):
     # Short K against many weight-row tiles: every CTA of the tcgen05 kernel works through several (tile, K run)s -- runs of
     # ONE unit (K = 64: a warp group then has no unit of its own in every other run), whole-tile runs in the middle of a
